@@ -1,0 +1,324 @@
+// exact.cuh -- the reference-order FP64 evaluation of every interpolation method, per query.
+//
+// This is the "exact path": one query evaluated with the reference CPU class's operation order
+// (GridH.cpp, cited per function), every FP64 operation spelled with a round-to-nearest intrinsic so
+// that nvcc cannot contract a*b+c into an FMA.  The reference's discrete decisions -- floor/round
+// centre, candidate enumeration order, strict-'<' tie breaks -- are decided by last-bit FP64 noise
+// (SURVEY.md section 0, facts 3-4), so they are only reproducible this way.  Bilinear, bicubic and
+// all neighbour selections come out bit-identical to the CPU reference; kriging differs only through
+// exp() (CUDA's is <=1 ulp, glibc's is correctly rounded), i.e. ~1e-10 m.
+//
+// The tiled fast paths (upsample.cu, fill.cu) handle clean stencils in bulk and call into this file
+// for every output whose footprint holds a NaN.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace auvi {
+
+enum Method : int { BILINEAR = 0, CUBIC = 1, KRIGING = 2, NN = 3, IDW = 4 };
+
+constexpr int kMaxRadius = 10;   // GridH.cpp:275, :339
+constexpr int kMaxCand   = 45;   // 3 + 2*(2*10+1): the most the early-terminating search can hold
+
+// Read-only view of the depth grid (row-major, row 0 = min_lat, GridD.cu:65-75).  A view may cover
+// only rows [row0, row0+rows) of the global grid (multi-GPU slabs); all index logic uses the global
+// dimensions, only the final address subtracts row0.
+template <typename T>
+struct GridView {
+    const T* __restrict__ z;
+    int n_lat, n_lon;            // global dimensions
+    int64_t ld;                  // elements between consecutive rows (>= n_lon)
+    int row0;                    // first global row held in z
+    double min_lon, max_lon, min_lat, max_lat;
+    double lon_step, lat_step;   // (max-min)/(n-1), GridH.cpp:156-157 / GridD.cu:52-53
+
+    __device__ __forceinline__ double at(int j, int i) const {
+        return static_cast<double>(__ldg(z + static_cast<int64_t>(j - row0) * ld + i));
+    }
+};
+
+// ---- contraction-proof FP64 arithmetic ---------------------------------------------------------
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
+__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+template <typename T>
+__device__ __forceinline__ bool outside(const GridView<T>& g, double lon, double lat) {
+    return lon < g.min_lon || lon > g.max_lon || lat < g.min_lat || lat > g.max_lat;   // GridH.cpp:162
+}
+// Grid-space coordinate, GridH.cpp:167-168.
+__device__ __forceinline__ double to_index_space(double c, double lo, double step) {
+    return ddiv(dsub(c, lo), step);
+}
+
+// Mean of the non-NaN members of four values, summed a,b,c,d in order (GridH.cpp:10-18).
+__device__ __forceinline__ double mean_valid4(double a, double b, double c, double d) {
+    double s = 0.0; int n = 0;
+    if (!isnan(a)) { s = dadd(s, a); ++n; }
+    if (!isnan(b)) { s = dadd(s, b); ++n; }
+    if (!isnan(c)) { s = dadd(s, c); ++n; }
+    if (!isnan(d)) { s = dadd(s, d); ++n; }
+    return n ? ddiv(s, static_cast<double>(n)) : qnan();
+}
+
+// ---- bilinear, GridH.cpp:160-210 ----------------------------------------------------------------
+template <typename T>
+__device__ double exact_bilinear(const GridView<T>& g, double x, double y) {
+    int x0 = static_cast<int>(floor(x)), y0 = static_cast<int>(floor(y));
+    int x1 = min(x0 + 1, g.n_lon - 1), y1 = min(y0 + 1, g.n_lat - 1);
+    double wx = dsub(x, static_cast<double>(x0)), wy = dsub(y, static_cast<double>(y0));
+    double a = g.at(y0, x0), b = g.at(y0, x1), c = g.at(y1, x0), d = g.at(y1, x1);
+    if (isnan(a) || isnan(b) || isnan(c) || isnan(d)) return mean_valid4(a, b, c, d);
+    double ux = dsub(1.0, wx);
+    double lo = dadd(dmul(ux, a), dmul(wx, b));
+    double hi = dadd(dmul(ux, c), dmul(wx, d));
+    return dadd(dmul(dsub(1.0, wy), lo), dmul(wy, hi));
+}
+
+// Catmull-Rom in the reference's polynomial form and summation order, GridH.cpp:215-217:
+// 0.5*(2*p1 + (-p0+p2)*t + (2*p0-5*p1+4*p2-p3)*t*t + (-p0+3*p1-3*p2+p3)*t*t*t)
+__device__ __forceinline__ double catmull_rom_exact(double p0, double p1, double p2, double p3, double t) {
+    double lin = dmul(dadd(-p0, p2), t);
+    double qc  = dsub(dadd(dsub(dmul(2.0, p0), dmul(5.0, p1)), dmul(4.0, p2)), p3);
+    double quad = dmul(dmul(qc, t), t);
+    double cc  = dadd(dsub(dadd(-p0, dmul(3.0, p1)), dmul(3.0, p2)), p3);
+    double cub = dmul(dmul(dmul(cc, t), t), t);
+    return dmul(0.5, dadd(dadd(dadd(dmul(2.0, p1), lin), quad), cub));
+}
+
+// ---- ring search, GridH.cpp:24-118 ---------------------------------------------------------------
+// Candidates are kept as (distance, packed offset); values are re-read for the few that survive.
+struct Cands {
+    double d[kMaxCand];
+    int16_t code[kMaxCand];      // (dj+10)*32 + (di+10), offsets from the search centre
+    int n;
+};
+__device__ __forceinline__ int16_t pack_off(int di, int dj) { return static_cast<int16_t>((dj + 10) * 32 + (di + 10)); }
+__device__ __forceinline__ int off_i(int16_t c) { return (c & 31) - 10; }
+__device__ __forceinline__ int off_j(int16_t c) { return (c >> 5) - 10; }
+
+template <typename T>
+__device__ __forceinline__ void consider(const GridView<T>& g, int ci, int cj, int di, int dj,
+                                         double x, double y, Cands& c) {
+    int i = ci + di, j = cj + dj;
+    if (isnan(g.at(j, i))) return;
+    double ddi = dsub(dadd(static_cast<double>(i), 0.5), x);     // (i + 0.5) - x, :42-44
+    double ddj = dsub(dadd(static_cast<double>(j), 0.5), y);
+    c.d[c.n] = dsqrt(dadd(dmul(ddi, ddi), dmul(ddj, ddj)));
+    c.code[c.n] = pack_off(di, dj);
+    ++c.n;
+}
+
+template <typename T>
+__device__ void ring_search(const GridView<T>& g, double x, double y, int ci, int cj, Cands& c) {
+    c.n = 0;
+    consider(g, ci, cj, 0, 0, x, y, c);                           // centre first
+    for (int r = 1; r <= kMaxRadius; ++r) {
+        const bool top_ok = cj - r >= 0, bot_ok = cj + r < g.n_lat;
+        for (int dx = -r; dx <= r; ++dx) {                        // top before bottom, per column
+            int i = ci + dx;
+            if (i < 0 || i >= g.n_lon) continue;
+            if (top_ok) consider(g, ci, cj, dx, -r, x, y, c);
+            if (bot_ok) consider(g, ci, cj, dx, +r, x, y, c);
+        }
+        if (c.n >= 4) break;
+        const bool lef_ok = ci - r >= 0, rig_ok = ci + r < g.n_lon;
+        for (int dy = -r + 1; dy <= r - 1; ++dy) {                // left before right, per row
+            int j = cj + dy;
+            if (j < 0 || j >= g.n_lat) continue;
+            if (lef_ok) consider(g, ci, cj, -r, dy, x, y, c);
+            if (rig_ok) consider(g, ci, cj, +r, dy, x, y, c);
+        }
+        if (c.n >= 4) break;
+    }
+}
+
+// Partial selection sort WITH SWAPS and strict '<' (GridH.cpp:123-140): the swap, not a stable
+// shift, decides which of two exactly tied candidates is taken, so it is reproduced literally.
+__device__ __forceinline__ void pick_four(Cands& c) {
+    for (int m = 0; m < 4; ++m) {
+        int best = m;
+        for (int k = m + 1; k < c.n; ++k)
+            if (c.d[k] < c.d[best]) best = k;
+        double td = c.d[m]; c.d[m] = c.d[best]; c.d[best] = td;
+        int16_t tc = c.code[m]; c.code[m] = c.code[best]; c.code[best] = tc;
+    }
+}
+
+// Outcome of a search: up to four cells (global indices), their values and distances.
+struct Picked {
+    int i[4], j[4];
+    double v[4], d[4];
+    int found;                   // total candidates seen by the search (GridH's `found`)
+};
+
+template <typename T>
+__device__ __forceinline__ void gather_picked(const GridView<T>& g, int ci, int cj, const Cands& c, Picked& p) {
+    p.found = c.n;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < c.n) {
+            p.i[k] = ci + off_i(c.code[k]); p.j[k] = cj + off_j(c.code[k]);
+            p.v[k] = g.at(p.j[k], p.i[k]);  p.d[k] = c.d[k];
+        } else {
+            p.i[k] = -1; p.j[k] = -1; p.v[k] = qnan(); p.d[k] = qnan();
+        }
+    }
+}
+
+// found < 4: mean of what was found, in enumeration order (GridH.cpp:291-298, :350-356).
+__device__ __forceinline__ double mean_found(const Picked& p) {
+    double s = 0.0;
+    for (int k = 0; k < p.found && k < 4; ++k) s = dadd(s, p.v[k]);
+    return p.found > 0 ? ddiv(s, static_cast<double>(p.found)) : qnan();
+}
+
+template <typename T>
+__device__ __forceinline__ void search_and_pick(const GridView<T>& g, double x, double y, int ci, int cj, Picked& p) {
+    Cands c;
+    ring_search(g, x, y, ci, cj, c);
+    if (c.n >= 4) pick_four(c);
+    gather_picked(g, ci, cj, c, p);
+}
+
+// ---- bicubic with 4-nearest-mean fallback, GridH.cpp:223-319 ---------------------------------------
+template <typename T>
+__device__ double exact_cubic(const GridView<T>& g, double x, double y, Picked* out_sel) {
+    int xi = static_cast<int>(floor(x)), yi = static_cast<int>(floor(y));
+    double tx = dsub(x, static_cast<double>(xi)), ty = dsub(y, static_cast<double>(yi));
+    double col[4];
+    bool dirty = false;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        int jj = clampi(yi - 1 + m, 0, g.n_lat - 1);              // clamp-to-edge, :240-247
+        double p[4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            p[n] = g.at(jj, clampi(xi - 1 + n, 0, g.n_lon - 1));
+            dirty |= isnan(p[n]);
+        }
+        col[m] = catmull_rom_exact(p[0], p[1], p[2], p[3], tx);
+    }
+    if (!dirty) {
+        if (out_sel) out_sel->found = -2;                         // clean stencil: no search ran
+        return catmull_rom_exact(col[0], col[1], col[2], col[3], ty);
+    }
+    Picked p;
+    search_and_pick(g, x, y, xi, yi, p);                          // floor centre, :281-289
+    if (out_sel) *out_sel = p;
+    if (p.found < 4) return mean_found(p);
+    return mean_valid4(p.v[0], p.v[1], p.v[2], p.v[3]);
+}
+
+// Centre of the round-centred methods, GridH.cpp:333-336.
+__device__ __forceinline__ int round_centre(double c, int n) {
+    return clampi(static_cast<int>(round(c)), 0, n - 1);
+}
+
+__device__ __forceinline__ double variogram(double h) {           // GridH.cpp:371-376
+    return dadd(1.0, dmul(100.0, dsub(1.0, exp(ddiv(-h, 10.0)))));
+}
+
+// ---- ordinary kriging on the four picked cells, GridH.cpp:361-419 ----------------------------------
+template <typename T>
+__device__ double kriging_from_picked(const GridView<T>& g, const Picked& p, double lon, double lat) {
+    double px[4], py[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                                  // cell centres in degrees, :366-367
+        px[k] = dadd(g.min_lon, dmul(dadd(static_cast<double>(p.i[k]), 0.5), g.lon_step));
+        py[k] = dadd(g.min_lat, dmul(dadd(static_cast<double>(p.j[k]), 0.5), g.lat_step));
+    }
+    double M[5][6];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            double dx = dsub(px[a], px[b]), dy = dsub(py[a], py[b]);
+            M[a][b] = variogram(dsqrt(dadd(dmul(dx, dx), dmul(dy, dy))));
+        }
+        M[a][4] = 1.0; M[4][a] = 1.0;
+        double dx = dsub(px[a], lon), dy = dsub(py[a], lat);        // raw query lon/lat, :380
+        M[a][5] = variogram(dsqrt(dadd(dmul(dx, dx), dmul(dy, dy))));
+    }
+    M[4][4] = 0.0; M[4][5] = 1.0;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {                                   // Gauss-Jordan, no pivoting
+        double piv = M[r][r];
+        if (fabs(piv) < 1e-12) return mean_valid4(p.v[0], p.v[1], p.v[2], p.v[3]);
+#pragma unroll
+        for (int q = r; q < 6; ++q) M[r][q] = ddiv(M[r][q], piv);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            if (k == r) continue;
+            double f = M[k][r];
+#pragma unroll
+            for (int q = r; q < 6; ++q) M[k][q] = dsub(M[k][q], dmul(f, M[r][q]));
+        }
+    }
+    double out = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out = dadd(out, dmul(M[k][5], p.v[k]));
+    return out;
+}
+
+// ---- EXTENSIONS: NN and IDW over the same selection ---------------
+__device__ __forceinline__ void nearest_first(Picked& p) {          // found < 4: first strict minimum
+    int m = p.found < 4 ? p.found : 4, best = 0;
+    for (int k = 1; k < m; ++k) if (p.d[k] < p.d[best]) best = k;
+    if (best) {
+        double t = p.v[0]; p.v[0] = p.v[best]; p.v[best] = t;
+        t = p.d[0]; p.d[0] = p.d[best]; p.d[best] = t;
+        int u = p.i[0]; p.i[0] = p.i[best]; p.i[best] = u;
+        u = p.j[0]; p.j[0] = p.j[best]; p.j[best] = u;
+    }
+}
+
+// IDW power 2 over min(found,4) picks.  Weights in FP32 through the SFU reciprocal (north_star:
+// "FP32 FMA/SFU distance-weight math"); the SELECTION above stays FP64-exact.  d == 0 -> that value.
+__device__ __forceinline__ double idw_from_picked(const Picked& p) {
+    int m = p.found < 4 ? p.found : 4;
+    float num = 0.f, den = 0.f;
+    // centre the values so the FP32 weighted mean keeps ~1e-7 relative accuracy on 10 km depths
+    const double ref = p.v[0];
+    for (int k = 0; k < m; ++k) {
+        if (p.d[k] == 0.0) return p.v[k];
+        float d = static_cast<float>(p.d[k]);
+        float w = __frcp_rn(d * d);
+        num = fmaf(w, static_cast<float>(p.v[k] - ref), num);
+        den += w;
+    }
+    return ref + static_cast<double>(__fdividef(num, den));
+}
+
+// ---- one query, any method --------------------------------------------------------------------------
+// lon/lat are the raw query coordinates; x/y their index-space images (precomputed by the caller so
+// that lattice kernels can take them from per-axis tables).  NaN x or y means out of bounds.
+template <typename T>
+__device__ double interp_exact(const GridView<T>& g, int method, double lon, double lat,
+                               double x, double y, Picked* sel) {
+    if (sel) { sel->found = -1; for (int k = 0; k < 4; ++k) { sel->i[k] = -1; sel->j[k] = -1; } }
+    if (isnan(x) || isnan(y)) return qnan();
+    if (method == BILINEAR) { if (sel) sel->found = -2; return exact_bilinear(g, x, y); }
+    if (method == CUBIC) return exact_cubic(g, x, y, sel);
+    Picked p;
+    int ci = round_centre(x, g.n_lon), cj = round_centre(y, g.n_lat);
+    search_and_pick(g, x, y, ci, cj, p);
+    double out;
+    if (method == KRIGING) {
+        out = p.found < 4 ? mean_found(p) : kriging_from_picked(g, p, lon, lat);
+    } else if (method == NN) {
+        if (p.found < 4) nearest_first(p);
+        out = p.found > 0 ? p.v[0] : qnan();
+    } else {
+        out = p.found > 0 ? idw_from_picked(p) : qnan();
+    }
+    if (sel) *sel = p;
+    return out;
+}
+
+}  // namespace auvi

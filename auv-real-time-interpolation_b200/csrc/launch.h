@@ -1,0 +1,64 @@
+// launch.h -- host-side descriptors and the launch entry points each kernel file exports to api.cu.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "exact.cuh"
+
+namespace auvi {
+
+enum DType : int { DT_F64 = 0, DT_F32 = 1 };
+
+// How a lattice axis turns an integer index into a coordinate (both are reference driver code):
+//   AXIS_EXPANDED: c = lo + k*(hi-lo)/(new_n-1)          test_interpolation.cpp:99-106 (Grid A)
+//   AXIS_NODES:    c = lo + k*step, step=(hi-lo)/(n-1)   test_gebco.cpp:72-81          (Grid B)
+enum AxisKind : int { AXIS_EXPANDED = 0, AXIS_NODES = 1 };
+
+// Device-resident grid (or a row slab of it) as the C-ABI holds it.
+struct GridDesc {
+    const void* z = nullptr;       // device pointer, row-major, row 0 = min_lat
+    int dtype = DT_F64;
+    int n_lat = 0, n_lon = 0;      // GLOBAL dimensions
+    int64_t ld = 0;                // elements between consecutive rows (>= n_lon)
+    int row0 = 0, rows = 0;        // slab held in z: global rows [row0, row0+rows)
+    double min_lon = 0, max_lon = 0, min_lat = 0, max_lat = 0;
+    double lon_step = 0, lat_step = 0;
+};
+
+template <typename T>
+inline GridView<T> make_view(const GridDesc& d) {
+    GridView<T> v;
+    v.z = static_cast<const T*>(d.z);
+    v.n_lat = d.n_lat; v.n_lon = d.n_lon; v.ld = d.ld; v.row0 = d.row0;
+    v.min_lon = d.min_lon; v.max_lon = d.max_lon; v.min_lat = d.min_lat; v.max_lat = d.max_lat;
+    v.lon_step = d.lon_step; v.lat_step = d.lat_step;
+    return v;
+}
+
+// Per-axis query tables of a separable lattice, one entry per OUTPUT index.  Built once on the host
+// with the reference drivers' exact expressions (api.cu), so every floor/round/tie decision
+// downstream sees the same last-bit FP64 noise the reference CPU path sees.
+struct AxisTables {
+    const double* coord = nullptr; // device: raw lon (or lat) of output index k
+    const double* pos = nullptr;   // device: index-space image (c-min)/step; NaN when out of bounds
+    const int* base = nullptr;     // device: floor(pos); for out-of-bounds entries the nearest valid one
+    const int* h_base = nullptr;   // host copy of base (tile sizing)
+    int n = 0;                     // number of output indices
+};
+
+// points.cu
+cudaError_t launch_points(const GridDesc& d, int method, const double* pts, int64_t stride_dbl, int64_t n,
+                          double* out, int32_t* sel, int32_t* found, cudaStream_t st);
+
+// upsample.cu -- lattice mode: out[(J-row_begin)*out_ld + I] for J in [row_begin,row_end), all I.
+// fill != 0: cells whose own grid value is valid are passed through (Grid-B gap fill on AXIS_NODES).
+// tmap may be null (no TMA: row pitch not a multiple of 16 B); sel (optional) is n x 8 int32.
+cudaError_t launch_lattice(const GridDesc& d, int method, const AxisTables& lat, const AxisTables& lon,
+                           int64_t row_begin, int64_t row_end, void* out, int64_t out_ld,
+                           int fill, int32_t* sel, const CUtensorMap* tmap_template,
+                           cudaStream_t st, int* launches);
+
+// Encodes a 2-D tiled tensor map over the grid slab; returns false when TMA cannot address it.
+bool make_grid_tensor_map(const GridDesc& d, int box_w, int box_h, CUtensorMap* out);
+
+}  // namespace auvi

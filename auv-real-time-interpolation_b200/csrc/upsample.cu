@@ -1,0 +1,374 @@
+// upsample.cu -- lattice mode: every output cell (J,I) of a separable query lattice.
+//
+// Replaces, for lattice-shaped query sets, the reference's per-point loop
+// GridH::batch*Interpolate (GridH.cpp:422-448) / GridD::batch* (GridD.cu:95-236) as driven by
+// generateExpandedGridQueryPoints (test_interpolation.cpp:91-109, Grid A upsampling) and by the
+// grid-node queries of test_gebco.cpp:72-81,150-160 (Grid B gap fill).  The query coordinates are
+// never materialised as 24-byte Points: they live in two per-axis FP64 tables (launch.h AxisTables).
+//
+// Two kernels:
+//
+//  upsample_tiled_kernel  (bilinear / bicubic) -- the HBM-bound fast path.
+//     CTA = 256 threads = 256 consecutive output columns x TJ output rows.  The input footprint of
+//     the tile (+ stencil halo) is staged into shared memory by ONE TMA 2-D box load
+//     (cp.async.bulk.tensor, zero-filled outside the grid, then patched to the reference's
+//     clamp-to-edge rule) or, when TMA cannot address the grid, by coalesced loads.
+//     Each thread owns one output column: its column base/fraction come from the longitude table,
+//     it keeps the horizontal pass of four consecutive input rows in registers and slides that
+//     window down as the (warp-uniform) latitude table advances, so every output costs one
+//     shared-memory read sweep / f_lat + one 4-tap vertical combine + one coalesced store.
+//     FP64 grids are evaluated in the reference's exact operation order (bit-identical results);
+//     FP32 grids use FP32 tap weights (|err| ~1e-7 relative).  Any output whose stencil touches a
+//     NaN (or lies out of bounds) comes out NaN and is re-evaluated by the exact path (exact.cuh),
+//     which reproduces the reference's ring-search fallback.
+//
+//  lattice_exact_kernel   (kriging / NN / IDW, and the gap-fill modes) -- one thread per output,
+//     exact path; with FILL it passes valid cells through untouched.
+//
+// Algorithmic HBM bytes per output cell: s_out + s_in/(f_lat*f_lon).
+#include "exact.cuh"
+#include "launch.h"
+#include "tma.cuh"
+
+namespace auvi {
+
+constexpr int kTileCols = 256;     // output columns per CTA = threads per CTA
+constexpr int kTileRowsMax = 128;  // output rows per CTA (upper bound; host picks TJ <= this)
+
+struct AxisDev {
+    const double* coord;
+    const double* pos;
+    const int* base;
+    int n;
+};
+
+template <typename T>
+struct TileParams {
+    GridView<T> g;
+    AxisDev lat, lon;
+    int64_t row_begin, row_end;    // output rows [row_begin,row_end)
+    T* out;
+    int64_t out_ld;
+    int tj;                        // output rows per CTA
+    int bw, bh;                    // shared-memory input box (elements)
+    int use_tma;
+};
+
+__device__ __forceinline__ void cr_weights(float t, float& w0, float& w1, float& w2, float& w3) {
+    // Catmull-Rom tap weights (the expansion of GridH.cpp:215-217 by tap).
+    float t2 = t * t, t3 = t2 * t;
+    w0 = 0.5f * (-t + 2.f * t2 - t3);
+    w1 = 0.5f * (2.f - 5.f * t2 + 3.f * t3);
+    w2 = 0.5f * (t + 4.f * t2 - 3.f * t3);
+    w3 = 0.5f * (-t2 + t3);
+}
+
+template <typename T> __device__ __forceinline__ void store_stream(T* p, T v);
+template <> __device__ __forceinline__ void store_stream<float>(float* p, float v) { __stcs(p, v); }
+template <> __device__ __forceinline__ void store_stream<double>(double* p, double v) { __stcs(p, v); }
+
+template <typename T, int METHOD>
+__global__ void __launch_bounds__(kTileCols, 4)
+upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const TileParams<T> p) {
+    constexpr bool kCubic = (METHOD == CUBIC);
+    constexpr int LO = kCubic ? 1 : 0;            // taps start at base-LO
+    constexpr int TAPS = kCubic ? 4 : 2;
+    constexpr bool kF64 = sizeof(T) == 8;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* tile = reinterpret_cast<T*>(smem_raw);                      // [bh][bw]
+    __shared__ uint64_t bar;
+    __shared__ int s_top[kTileRowsMax];                            // local row of the first tap
+    __shared__ double s_ty[kTileRowsMax];                          // frac(pos_y), NaN if out of bounds
+    __shared__ float4 s_wy[kTileRowsMax];                          // FP32 vertical tap weights
+
+    const int tid = threadIdx.x;
+    const int W = p.lon.n;
+    const int I0 = blockIdx.x * kTileCols;
+    const int64_t J0 = p.row_begin + static_cast<int64_t>(blockIdx.y) * p.tj;
+    const int nJ = static_cast<int>(min<int64_t>(p.tj, p.row_end - J0));
+    const int c0 = __ldg(p.lon.base + I0) - LO;                    // global column of tile column 0
+    const int r0 = __ldg(p.lat.base + J0) - LO;                    // global row of tile row 0
+    const int bw = p.bw, bh = p.bh;
+
+    // ---- stage the input box -------------------------------------------------------------------
+    if (p.use_tma) {
+        if (tid == 0) { prefetch_tmap(&tmap); mbar_init(&bar, 1); }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bar, static_cast<uint32_t>(bw * bh * sizeof(T)));
+            tma_load_2d(tile, &tmap, c0, r0 - p.g.row0, &bar);
+        }
+    } else {
+        for (int k = tid; k < bw * bh; k += kTileCols) {           // coalesced, clamp-to-edge
+            int lr = k / bw, lc = k - lr * bw;
+            int gr = clampi(r0 + lr, 0, p.g.n_lat - 1), gc = clampi(c0 + lc, 0, p.g.n_lon - 1);
+            tile[k] = __ldg(p.g.z + static_cast<int64_t>(gr - p.g.row0) * p.g.ld + gc);
+        }
+    }
+
+    // ---- per-row and per-column setup (overlaps the TMA flight) ---------------------------------
+    if (tid < nJ) {
+        const double py = __ldg(p.lat.pos + J0 + tid);
+        const int by = __ldg(p.lat.base + J0 + tid);
+        const double ty = dsub(py, static_cast<double>(by));       // NaN stays NaN
+        s_top[tid] = by - LO - r0;
+        s_ty[tid] = ty;
+        float4 w;
+        if (kCubic) cr_weights(static_cast<float>(ty), w.x, w.y, w.z, w.w);
+        else { w.x = 1.f - static_cast<float>(ty); w.y = static_cast<float>(ty); w.z = 0.f; w.w = 0.f; }
+        s_wy[tid] = w;
+    }
+    const int I = I0 + tid;
+    const bool active = I < W;
+    double px = qnan();
+    int bx = c0 + LO;
+    if (active) { px = __ldg(p.lon.pos + I); bx = __ldg(p.lon.base + I); }
+    const double txd = active ? dsub(px, static_cast<double>(bx)) : 0.0;
+    const int ox = bx - LO - c0;
+    float wx0 = 0.f, wx1 = 0.f, wx2 = 0.f, wx3 = 0.f;
+    if (!kF64) {
+        if (kCubic) cr_weights(static_cast<float>(txd), wx0, wx1, wx2, wx3);
+        else { wx0 = 1.f - static_cast<float>(txd); wx1 = static_cast<float>(txd); }
+    }
+
+    if (p.use_tma) {
+        mbar_wait(&bar, 0);
+        // The reference clamps stencil indices to the grid edge (GridH.cpp:242-247, :172-173); TMA
+        // zero-fills instead, so border tiles copy the edge row/column into their out-of-grid halo.
+        const bool border = c0 < 0 || c0 + bw > p.g.n_lon || r0 < 0 || r0 + bh > p.g.n_lat;
+        if (border) {
+            for (int k = tid; k < bw * bh; k += kTileCols) {
+                int lr = k / bw, lc = k - lr * bw;
+                int gr = r0 + lr, gc = c0 + lc;
+                int cr = clampi(gr, 0, p.g.n_lat - 1), cc = clampi(gc, 0, p.g.n_lon - 1);
+                if (cr != gr || cc != gc) {
+                    int sr = cr - r0, sc = cc - c0;                // in-grid source, never rewritten
+                    if (sr >= 0 && sr < bh && sc >= 0 && sc < bw) tile[k] = tile[sr * bw + sc];
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- horizontal pass of one tile row for this thread's column --------------------------------
+    auto hrow = [&](int lr) -> T {
+        lr = min(lr, bh - 1);                                      // window rows past the box are unused
+        const T* r = tile + lr * bw + ox;
+        if constexpr (kF64) {
+            if constexpr (kCubic) return catmull_rom_exact(r[0], r[1], r[2], r[3], txd);
+            else return dadd(dmul(dsub(1.0, txd), r[0]), dmul(txd, r[1]));
+        } else {
+            if constexpr (kCubic) return fmaf(wx3, r[3], fmaf(wx2, r[2], fmaf(wx1, r[1], wx0 * r[0])));
+            else return fmaf(wx1, r[1], wx0 * r[0]);
+        }
+    };
+
+    T h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+    int top = -(1 << 20);
+    T* out_col = p.out + (J0 - p.row_begin) * p.out_ld + I;
+    for (int jr = 0; jr < nJ; ++jr) {
+        const int t = s_top[jr];                                   // warp-uniform
+        if (t != top) {
+            const int shift = t - top;
+            if (shift == 1) { h0 = h1; h1 = h2; h2 = h3; h3 = hrow(t + TAPS - 1); if (!kCubic) h1 = hrow(t + 1); }
+            else if (shift == 2 && kCubic) { h0 = h2; h1 = h3; h2 = hrow(t + 2); h3 = hrow(t + 3); }
+            else {
+                h0 = hrow(t); h1 = hrow(t + 1);
+                if (kCubic) { h2 = hrow(t + 2); h3 = hrow(t + 3); }
+            }
+            top = t;
+        }
+        T v;
+        if constexpr (kF64) {
+            const double ty = s_ty[jr];
+            if constexpr (kCubic) v = catmull_rom_exact(h0, h1, h2, h3, ty);
+            else v = dadd(dmul(dsub(1.0, ty), h0), dmul(ty, h1));
+        } else {
+            const float4 w = s_wy[jr];
+            if constexpr (kCubic) v = fmaf(w.w, h3, fmaf(w.z, h2, fmaf(w.y, h1, w.x * h0)));
+            else v = fmaf(w.y, h1, w.x * h0);
+        }
+        if (active) {
+            if (isnan(v)) {                                        // NaN in the footprint, or out of bounds
+                const int64_t J = J0 + jr;
+                const double py = __ldg(p.lat.pos + J);
+                v = static_cast<T>(interp_exact<T>(p.g, METHOD, __ldg(p.lon.coord + I), __ldg(p.lat.coord + J),
+                                                   px, py, nullptr));
+            }
+            store_stream<T>(out_col, v);
+        }
+        out_col += p.out_ld;
+    }
+}
+
+// ---- one thread per output, exact path ----------------------------------------------------------
+template <typename T, int METHOD, bool FILL>
+__global__ void __launch_bounds__(256)
+lattice_exact_kernel(const GridView<T> g, const AxisDev lat, const AxisDev lon, int64_t row_begin,
+                     int64_t row_end, T* __restrict__ out, int64_t out_ld, int32_t* __restrict__ sel) {
+    const int W = lon.n;
+    const int64_t total = (row_end - row_begin) * W;
+    for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < total;
+         k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t jr = k / W;
+        const int I = static_cast<int>(k - jr * W);
+        const int64_t J = row_begin + jr;
+        Picked pk;
+        pk.found = -3;                                             // -3: valid cell passed through
+        double v;
+        bool done = false;
+        if (FILL) {
+            v = g.at(static_cast<int>(J), I);
+            done = !isnan(v);
+        }
+        if (!done) {
+            v = interp_exact<T>(g, METHOD, __ldg(lon.coord + I), __ldg(lat.coord + J), __ldg(lon.pos + I),
+                                __ldg(lat.pos + J), sel ? &pk : nullptr);
+        }
+        store_stream<T>(out + jr * out_ld + I, static_cast<T>(v));
+        if (sel) {
+            int32_t* s = sel + k * 9;
+            const bool has = pk.found >= 0;
+            s[0] = pk.found;
+            for (int q = 0; q < 4; ++q) { s[1 + 2 * q] = has ? pk.i[q] : -1; s[2 + 2 * q] = has ? pk.j[q] : -1; }
+        }
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+bool make_grid_tensor_map(const GridDesc& d, int box_w, int box_h, CUtensorMap* out) {
+    const size_t es = d.dtype == DT_F64 ? 8 : 4;
+    if (box_w > 256 || box_h > 256 || box_w < 1 || box_h < 1) return false;
+    if ((d.ld * es) % 16 != 0 || (reinterpret_cast<uintptr_t>(d.z) % 16) != 0) return false;
+    if ((box_w * es) % 16 != 0) return false;
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.n_lon), static_cast<cuuint64_t>(d.rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(d.ld * es)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, d.dtype == DT_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                    const_cast<void*>(d.z), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// Largest input span (in cells) any tile of `tile` consecutive outputs needs along one axis.
+static int max_span(const int* h_base, int64_t begin, int64_t end, int tile, int taps) {
+    int worst = 0;
+    for (int64_t a = begin; a < end; a += tile) {
+        int64_t b = (a + tile - 1 < end - 1) ? a + tile - 1 : end - 1;
+        int s = h_base[b] - h_base[a] + taps;
+        if (s > worst) worst = s;
+    }
+    return worst;
+}
+
+template <typename T, int METHOD>
+static cudaError_t launch_tiled(const GridDesc& d, const AxisTables& lat, const AxisTables& lon, int64_t row_begin,
+                                int64_t row_end, void* out, int64_t out_ld, cudaStream_t st) {
+    const int taps = METHOD == CUBIC ? 4 : 2;
+    const int lo = METHOD == CUBIC ? 1 : 0;
+    const size_t es = sizeof(T);
+    const int align = static_cast<int>(16 / es);
+    int tj = 64;
+    int bw = max_span(lon.h_base, 0, lon.n, kTileCols, taps);
+    bw = (bw + align - 1) / align * align;
+    int bh = max_span(lat.h_base, row_begin, row_end, tj, taps);
+    while (static_cast<size_t>(bw) * bh * es > 96 * 1024 && tj > 8) {       // keep >=2 CTAs/SM of smem
+        tj /= 2;
+        bh = max_span(lat.h_base, row_begin, row_end, tj, taps);
+    }
+    // slab check: every input row a tile touches (after the reference's clamp) must be resident
+    int need_lo = lat.h_base[row_begin] - lo, need_hi = lat.h_base[row_end - 1] - lo + taps - 1;
+    need_lo = need_lo < 0 ? 0 : need_lo;
+    need_hi = need_hi > d.n_lat - 1 ? d.n_lat - 1 : need_hi;
+    if (need_lo < d.row0 || need_hi >= d.row0 + d.rows) return cudaErrorInvalidValue;
+
+    TileParams<T> p;
+    p.g = make_view<T>(d);
+    p.lat = AxisDev{lat.coord, lat.pos, lat.base, lat.n};
+    p.lon = AxisDev{lon.coord, lon.pos, lon.base, lon.n};
+    p.row_begin = row_begin; p.row_end = row_end;
+    p.out = static_cast<T*>(out); p.out_ld = out_ld;
+    p.tj = tj; p.bw = bw; p.bh = bh;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    // TMA needs the whole slab to be exactly the tensor (rows outside the slab but inside the grid
+    // would be zero-filled silently), so it is only used when the slab is the full grid.
+    p.use_tma = (d.row0 == 0 && d.rows == d.n_lat && make_grid_tensor_map(d, bw, bh, &tmap)) ? 1 : 0;
+
+    const size_t smem = static_cast<size_t>(bw) * bh * es;
+    auto kern = upsample_tiled_kernel<T, METHOD>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid(static_cast<unsigned>((lon.n + kTileCols - 1) / kTileCols),
+              static_cast<unsigned>((row_end - row_begin + tj - 1) / tj));
+    kern<<<grid, kTileCols, smem, st>>>(tmap, p);
+    return cudaGetLastError();
+}
+
+template <typename T, int METHOD, bool FILL>
+static cudaError_t launch_exact(const GridDesc& d, const AxisTables& lat, const AxisTables& lon, int64_t row_begin,
+                                int64_t row_end, void* out, int64_t out_ld, int32_t* sel, cudaStream_t st) {
+    const int64_t total = (row_end - row_begin) * lon.n;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    lattice_exact_kernel<T, METHOD, FILL><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        make_view<T>(d), AxisDev{lat.coord, lat.pos, lat.base, lat.n}, AxisDev{lon.coord, lon.pos, lon.base, lon.n},
+        row_begin, row_end, static_cast<T*>(out), out_ld, sel);
+    return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t launch_lattice_t(const GridDesc& d, int method, const AxisTables& lat, const AxisTables& lon,
+                                    int64_t row_begin, int64_t row_end, void* out, int64_t out_ld, int fill,
+                                    int32_t* sel, cudaStream_t st) {
+    if (!fill && !sel) {
+        if (method == BILINEAR) return launch_tiled<T, BILINEAR>(d, lat, lon, row_begin, row_end, out, out_ld, st);
+        if (method == CUBIC) return launch_tiled<T, CUBIC>(d, lat, lon, row_begin, row_end, out, out_ld, st);
+    }
+#define AUVI_CASE(M)                                                                                         \
+    case M:                                                                                                  \
+        return fill ? launch_exact<T, M, true>(d, lat, lon, row_begin, row_end, out, out_ld, sel, st)        \
+                    : launch_exact<T, M, false>(d, lat, lon, row_begin, row_end, out, out_ld, sel, st);
+    switch (method) {
+        AUVI_CASE(BILINEAR) AUVI_CASE(CUBIC) AUVI_CASE(KRIGING) AUVI_CASE(NN) AUVI_CASE(IDW)
+        default: return cudaErrorInvalidValue;
+    }
+#undef AUVI_CASE
+}
+
+cudaError_t launch_lattice(const GridDesc& d, int method, const AxisTables& lat, const AxisTables& lon,
+                           int64_t row_begin, int64_t row_end, void* out, int64_t out_ld, int fill, int32_t* sel,
+                           const CUtensorMap*, cudaStream_t st, int* launches) {
+    if (row_end <= row_begin) return cudaSuccess;
+    if (launches) *launches += 1;
+    if (d.dtype == DT_F64)
+        return launch_lattice_t<double>(d, method, lat, lon, row_begin, row_end, out, out_ld, fill, sel, st);
+    return launch_lattice_t<float>(d, method, lat, lon, row_begin, row_end, out, out_ld, fill, sel, st);
+}
+
+}  // namespace auvi

@@ -1,0 +1,108 @@
+/* include/auvi.h -- the C ABI of libauvi.so, the B200-native replacement for the GPU half of
+ * devsaxena974/AUV-Real-Time-Interpolation (code/src/GridD.cu + code/src/kernels.cu).
+ *
+ * Everything the reference's host code needs from the device goes through these entry points:
+ * plain pointers and sizes, no C++/torch types.  include/GridD.h is the C++ class with the
+ * reference's own signatures written on top of it; INTEGRATION.md shows the binding a maintainer
+ * of the reference would add.  All functions return 0 on success, non-zero on failure with a
+ * message available from auvi_last_error().  There is no CPU fallback: without a CUDA device every
+ * compute call fails.
+ *
+ * Reference citations are file:line in /root/reference/code.
+ */
+#ifndef AUVI_H
+#define AUVI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct auvi_grid auvi_grid;   /* opaque: a depth grid resident on one GPU */
+
+/* Interpolation methods.  0-2 are the reference's three (include/GridD.h:69,77,85);
+ * 3-4 are extensions defined on the reference's own neighbour search. */
+enum { AUVI_BILINEAR = 0, AUVI_CUBIC = 1, AUVI_KRIGING = 2, AUVI_NN = 3, AUVI_IDW = 4 };
+/* Storage type of the depth grid and of lattice outputs. */
+enum { AUVI_F64 = 0, AUVI_F32 = 1 };
+/* How a lattice axis maps an output index to a coordinate:
+ *   AUVI_AXIS_EXPANDED  c = lo + k*(hi-lo)/(new_n-1), new_n = f*(n-1)+1  (test_interpolation.cpp:91-109)
+ *   AUVI_AXIS_NODES     c = lo + k*((hi-lo)/(n-1))                        (test_gebco.cpp:72-81)      */
+enum { AUVI_AXIS_EXPANDED = 0, AUVI_AXIS_NODES = 1 };
+
+/* ---- grid lifetime: replaces GridD::GridD + GridD::initialize (src/GridD.cu:41-83) and
+ *      GridD::cleanup / ~GridD (src/GridD.cu:59-62,86-92) ------------------------------------- */
+
+/* Upload a dense row-major host grid (row 0 = min_lat, as GridD.cu:67-72 flattens it).
+ * dtype = type of host_rowmajor and of the device copy.  device = CUDA ordinal. */
+int auvi_grid_create(const void* host_rowmajor, int dtype, int64_t n_lat, int64_t n_lon,
+                     double min_lon, double max_lon, double min_lat, double max_lat,
+                     int device, auvi_grid** out);
+
+/* Adopt (borrow, never free) a grid -- or a row slab of one -- already resident in device memory.
+ * dev_rows holds global rows [row0, row0+rows) with `ld` elements between rows; n_lat is the
+ * GLOBAL row count (multi-GPU row sharding: each rank passes its slab + halo). */
+int auvi_grid_adopt(const void* dev_rows, int dtype, int64_t n_lat, int64_t n_lon, int64_t ld,
+                    int64_t row0, int64_t rows,
+                    double min_lon, double max_lon, double min_lat, double max_lat,
+                    int device, auvi_grid** out);
+
+int auvi_grid_destroy(auvi_grid* g);      /* idempotent on NULL */
+
+/* ---- Point-list mode: replaces GridD::batch{Bilinear,Cubic,OrdinaryKriging}Interpolate
+ *      (src/GridD.cu:95-150,156-193,199-236) and the three kernels of src/kernels.cu:173-546 ---- */
+
+/* host_pts: n records of `stride_bytes` (24 for struct Point{lon,lat,elev}, include/Point.h:9-13);
+ * host_out_elev[n] receives the interpolated depth (NaN outside the bounds, kernels.cu:193-196).
+ * Synchronous; persistent pinned staging + device buffers are reused across calls. */
+int auvi_interp_points(auvi_grid* g, int method, const void* host_pts, int64_t n,
+                       int64_t stride_bytes, double* host_out_elev);
+
+/* Same on device-resident buffers, asynchronous on `stream` (a cudaStream_t, may be NULL).
+ * dev_sel (optional, n x 8 int32) / dev_found (optional, n int32) receive the neighbour selection
+ * {i0,j0,...,i3,j3} and candidate count (-1 outside, -2 no search needed) for parity checks. */
+int auvi_interp_points_device(auvi_grid* g, int method, const void* dev_pts, int64_t n,
+                              int64_t stride_bytes, double* dev_out_elev,
+                              int32_t* dev_sel, int32_t* dev_found, void* stream);
+
+/* ---- Lattice mode: the structured form of the same batches.  The query set is the separable
+ *      lattice the reference drivers build -- generateExpandedGridQueryPoints
+ *      (test_interpolation.cpp:91-109, axis kind EXPANDED, factor f => f*(n-1)+1 outputs per axis)
+ *      or the grid nodes of test_gebco.cpp:72-81,150-160 (axis kind NODES, factor 1) -- without
+ *      materialising 24-byte Points.  Output cell (J,I) equals what GridH::batch* returns for the
+ *      query {lon(I), lat(J)}.  Rows [row_begin,row_end) only: the unit of multi-GPU sharding. ---- */
+
+/* Output lattice dimensions for a grid and factors. */
+int auvi_lattice_dims(const auvi_grid* g, int axis_kind, int f_lat, int f_lon,
+                      int64_t* out_rows, int64_t* out_cols);
+
+/* Upsample (fill = 0) or gap-fill (fill = 1: cells whose own value is valid are copied through,
+ * NaN cells get method(query at that node); requires axis kind NODES and factors 1).
+ * dev_out: (row_end-row_begin) rows of out_ld elements of the grid's dtype.  Asynchronous on stream. */
+int auvi_lattice_device(auvi_grid* g, int method, int axis_kind, int f_lat, int f_lon, int fill,
+                        int64_t row_begin, int64_t row_end, void* dev_out, int64_t out_ld,
+                        int32_t* dev_sel9, void* stream);
+
+/* Host-buffer form: result rows are copied to host_out (dense, out_cols elements per row) inside
+ * the call; synchronous. */
+int auvi_lattice(auvi_grid* g, int method, int axis_kind, int f_lat, int f_lon, int fill,
+                 int64_t row_begin, int64_t row_end, void* host_out);
+
+/* ---- Error metrics on device: replaces meanAbsoluteError / rootMeanSquareError /
+ *      maxAbsoluteError (src/error_calculator.cpp:5-45), same NaN/denominator convention.
+ *      out3 = {MAE, RMSE, Max}; out_nan = number of NaN estimates. */
+int auvi_error_metrics_device(const void* dev_truth, const void* dev_est, int dtype, int64_t n,
+                              double* out3, int64_t* out_nan, void* stream);
+
+/* ---- diagnostics ------------------------------------------------------------------------------ */
+const char* auvi_last_error(void);          /* thread-local message of the last failure */
+float auvi_last_kernel_ms(const auvi_grid* g); /* device time of the last synchronous call's kernels */
+int64_t auvi_launch_count(void);            /* kernels launched by this library so far (process-wide) */
+int auvi_uses_tma(const auvi_grid* g);      /* 1 if the last lattice launch staged tiles by TMA */
+int auvi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUVI_H */
