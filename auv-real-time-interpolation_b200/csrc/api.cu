@@ -1,0 +1,449 @@
+// api.cu -- the C ABI of libauvi.so (include/auvi.h): grid lifetime, the host-buffer and
+// device-buffer forms of the three calling modes (point list, lattice, metrics), diagnostics.
+//
+// Replaces the host half of the reference's device class, code/src/GridD.cu:
+//   GridD::initialize  (:65-83)   -> auvi_grid_create        (one upload, grid stays resident)
+//   GridD::batch*      (:95-236)  -> auvi_interp_points      (persistent pinned staging + device
+//                                    buffers, chunked so H2D / kernel / D2H of successive chunks
+//                                    overlap on two streams; the reference mallocs, copies
+//                                    synchronously and frees on every call)
+//   GridD::cleanup     (:86-92)   -> auvi_grid_destroy
+// and adds the structured lattice mode (upsample.cu) for the query sets the reference drivers build.
+//
+// Host arithmetic that decides discrete outcomes (grid steps, lattice coordinates, index-space
+// images) is written with the reference's exact expressions and compiled with -ffp-contract=off
+// (Makefile): SURVEY.md section 0 facts 3-4.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/auvi.h"
+#include "launch.h"
+
+using namespace auvi;
+
+namespace {
+
+thread_local std::string t_error;
+std::atomic<int64_t> g_launches{0};
+
+int fail(const std::string& msg) { t_error = msg; return 1; }
+int fail_cuda(const char* what, cudaError_t e) {
+    t_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return 2;
+}
+#define AUVI_CUDA(call)                                                   \
+    do {                                                                  \
+        cudaError_t e_ = (call);                                          \
+        if (e_ != cudaSuccess) return fail_cuda(#call, e_);               \
+    } while (0)
+
+struct AxisOwned {
+    std::vector<double> coord, pos;
+    std::vector<int> base;
+    double* d_coord = nullptr;
+    double* d_pos = nullptr;
+    int* d_base = nullptr;
+    AxisTables view() const {
+        AxisTables t;
+        t.coord = d_coord; t.pos = d_pos; t.base = d_base; t.h_base = base.data();
+        t.n = static_cast<int>(coord.size());
+        return t;
+    }
+};
+
+constexpr int64_t kPointChunk = 1 << 20;            // queries per pipeline stage (16 MiB in, 8 MiB out)
+constexpr int64_t kLatticeChunkBytes = 256ll << 20; // device staging per pipeline stage, lattice host form
+
+}  // namespace
+
+struct auvi_grid {
+    GridDesc d;
+    int device = 0;
+    void* owned = nullptr;                            // device allocation we must free (create), else null
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t ev_k0[2] = {nullptr, nullptr}, ev_k1[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    // point-list staging (double-buffered)
+    double* h_in[2] = {nullptr, nullptr};             // pinned, packed {lon,lat}
+    double* h_out[2] = {nullptr, nullptr};            // pinned
+    double* d_in[2] = {nullptr, nullptr};
+    double* d_out[2] = {nullptr, nullptr};
+    // lattice host-form staging
+    void* d_rows[2] = {nullptr, nullptr};
+    size_t d_rows_bytes = 0;
+    // metrics scratch
+    void* d_scratch = nullptr;
+    double* d_result4 = nullptr;
+    std::map<long long, AxisOwned*> axes;             // key: which*2^40 + kind*2^32 + factor
+    float last_ms = 0.f;
+    int last_tma = 0;
+};
+
+namespace {
+
+int make_streams(auvi_grid* g) {
+    for (int k = 0; k < 2; ++k) {
+        AUVI_CUDA(cudaStreamCreateWithFlags(&g->st[k], cudaStreamNonBlocking));
+        AUVI_CUDA(cudaEventCreate(&g->ev_k0[k]));
+        AUVI_CUDA(cudaEventCreate(&g->ev_k1[k]));
+        AUVI_CUDA(cudaEventCreateWithFlags(&g->ev_done[k], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+int check_common(const auvi_grid* g, int method) {
+    if (!g) return fail("null grid handle");
+    if (method < AUVI_BILINEAR || method > AUVI_IDW) return fail("unknown interpolation method");
+    return 0;
+}
+
+// Per-axis lattice tables.  `which` 0 = longitude (columns), 1 = latitude (rows).
+int get_axis(auvi_grid* g, int which, int kind, int factor, AxisOwned** out) {
+    const long long key = (static_cast<long long>(which) << 40) | (static_cast<long long>(kind) << 32) | factor;
+    auto it = g->axes.find(key);
+    if (it != g->axes.end()) { *out = it->second; return 0; }
+    const int n = which == 0 ? g->d.n_lon : g->d.n_lat;
+    const double lo = which == 0 ? g->d.min_lon : g->d.min_lat;
+    const double hi = which == 0 ? g->d.max_lon : g->d.max_lat;
+    const double step = which == 0 ? g->d.lon_step : g->d.lat_step;
+    if (factor < 1) return fail("lattice factor must be >= 1");
+    if (kind == AUVI_AXIS_NODES && factor != 1) return fail("AUVI_AXIS_NODES requires factor 1");
+    const int64_t n_out64 = static_cast<int64_t>(factor) * (n - 1) + 1;
+    if (n_out64 > (1ll << 30)) return fail("lattice axis too long");
+    const int n_out = static_cast<int>(n_out64);
+    AxisOwned* a = new (std::nothrow) AxisOwned;
+    if (!a) return fail("out of host memory");
+    a->coord.resize(n_out); a->pos.resize(n_out); a->base.resize(n_out);
+    for (int k = 0; k < n_out; ++k) {
+        double c;
+        if (kind == AUVI_AXIS_NODES) c = lo + k * step;                       // test_gebco.cpp:79-80
+        else c = lo + k * (hi - lo) / (n_out - 1);                            // test_interpolation.cpp:99-104
+        const double p = (c - lo) / step;                                      // GridH.cpp:167-168
+        const bool out_of_bounds = c < lo || c > hi;                           // GridH.cpp:162 (per axis)
+        a->coord[k] = c;
+        a->pos[k] = out_of_bounds ? std::nan("") : p;
+        int b = static_cast<int>(std::floor(p));
+        a->base[k] = b < 0 ? 0 : (b > n - 1 ? n - 1 : b);
+    }
+    cudaError_t e;
+    if ((e = cudaMalloc(&a->d_coord, sizeof(double) * n_out)) != cudaSuccess ||
+        (e = cudaMalloc(&a->d_pos, sizeof(double) * n_out)) != cudaSuccess ||
+        (e = cudaMalloc(&a->d_base, sizeof(int) * n_out)) != cudaSuccess ||
+        (e = cudaMemcpy(a->d_coord, a->coord.data(), sizeof(double) * n_out, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(a->d_pos, a->pos.data(), sizeof(double) * n_out, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(a->d_base, a->base.data(), sizeof(int) * n_out, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        cudaFree(a->d_coord); cudaFree(a->d_pos); cudaFree(a->d_base);
+        delete a;
+        return fail_cuda("axis table upload", e);
+    }
+    g->axes[key] = a;
+    *out = a;
+    return 0;
+}
+
+int fill_desc(GridDesc& d, int dtype, int64_t n_lat, int64_t n_lon, double min_lon, double max_lon,
+              double min_lat, double max_lat) {
+    if (dtype != AUVI_F64 && dtype != AUVI_F32) return fail("dtype must be AUVI_F64 or AUVI_F32");
+    if (n_lat < 2 || n_lon < 2) return fail("grid needs at least 2 points per axis");
+    if (n_lat > (1ll << 30) || n_lon > (1ll << 30)) return fail("grid axis too long");
+    d.dtype = dtype;
+    d.n_lat = static_cast<int>(n_lat); d.n_lon = static_cast<int>(n_lon);
+    d.min_lon = min_lon; d.max_lon = max_lon; d.min_lat = min_lat; d.max_lat = max_lat;
+    d.lon_step = (max_lon - min_lon) / (d.n_lon - 1);                          // GridD.cu:52-53
+    d.lat_step = (max_lat - min_lat) / (d.n_lat - 1);
+    return 0;
+}
+
+int ensure_point_staging(auvi_grid* g) {
+    if (g->h_in[0]) return 0;
+    for (int k = 0; k < 2; ++k) {
+        AUVI_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g->h_in[k]), sizeof(double) * 2 * kPointChunk, cudaHostAllocDefault));
+        AUVI_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g->h_out[k]), sizeof(double) * kPointChunk, cudaHostAllocDefault));
+        AUVI_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->d_in[k]), sizeof(double) * 2 * kPointChunk));
+        AUVI_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->d_out[k]), sizeof(double) * kPointChunk));
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int auvi_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int auvi_version(void) { return 100; }
+const char* auvi_last_error(void) { return t_error.c_str(); }
+int64_t auvi_launch_count(void) { return g_launches.load(); }
+float auvi_last_kernel_ms(const auvi_grid* g) { return g ? g->last_ms : 0.f; }
+int auvi_uses_tma(const auvi_grid* g) { return g ? g->last_tma : 0; }
+
+int auvi_grid_create(const void* host_rowmajor, int dtype, int64_t n_lat, int64_t n_lon,
+                     double min_lon, double max_lon, double min_lat, double max_lat,
+                     int device, auvi_grid** out) {
+    if (!out) return fail("null output handle");
+    *out = nullptr;
+    if (!host_rowmajor) return fail("null host grid");
+    if (auvi_device_count() <= 0) return fail("no CUDA device: libauvi has no CPU fallback");
+    auvi_grid* g = new (std::nothrow) auvi_grid;
+    if (!g) return fail("out of host memory");
+    if (fill_desc(g->d, dtype, n_lat, n_lon, min_lon, max_lon, min_lat, max_lat)) { delete g; return 1; }
+    g->device = device;
+    const size_t es = dtype == AUVI_F64 ? 8 : 4;
+    // rows padded to a 16-byte pitch so that TMA can address any grid width
+    const int64_t ld = (n_lon * es + 15) / 16 * 16 / es;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(&g->owned, static_cast<size_t>(ld) * n_lat * es);
+    if (e == cudaSuccess)
+        e = cudaMemcpy2D(g->owned, ld * es, host_rowmajor, n_lon * es, n_lon * es, n_lat, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(g->owned); delete g; return fail_cuda("grid upload", e); }
+    g->d.z = g->owned; g->d.ld = ld; g->d.row0 = 0; g->d.rows = g->d.n_lat;
+    if (make_streams(g)) { auvi_grid_destroy(g); return 2; }
+    *out = g;
+    return 0;
+}
+
+int auvi_grid_adopt(const void* dev_rows, int dtype, int64_t n_lat, int64_t n_lon, int64_t ld,
+                    int64_t row0, int64_t rows,
+                    double min_lon, double max_lon, double min_lat, double max_lat,
+                    int device, auvi_grid** out) {
+    if (!out) return fail("null output handle");
+    *out = nullptr;
+    if (!dev_rows) return fail("null device grid");
+    if (auvi_device_count() <= 0) return fail("no CUDA device: libauvi has no CPU fallback");
+    if (ld < n_lon) return fail("ld must be >= n_lon");
+    if (row0 < 0 || rows < 1 || row0 + rows > n_lat) return fail("slab rows outside the grid");
+    auvi_grid* g = new (std::nothrow) auvi_grid;
+    if (!g) return fail("out of host memory");
+    if (fill_desc(g->d, dtype, n_lat, n_lon, min_lon, max_lon, min_lat, max_lat)) { delete g; return 1; }
+    g->device = device;
+    g->d.z = dev_rows; g->d.ld = ld; g->d.row0 = static_cast<int>(row0); g->d.rows = static_cast<int>(rows);
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete g; return fail_cuda("cudaSetDevice", e); }
+    if (make_streams(g)) { auvi_grid_destroy(g); return 2; }
+    *out = g;
+    return 0;
+}
+
+int auvi_grid_destroy(auvi_grid* g) {
+    if (!g) return 0;
+    cudaSetDevice(g->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : g->axes) {
+        cudaFree(kv.second->d_coord); cudaFree(kv.second->d_pos); cudaFree(kv.second->d_base);
+        delete kv.second;
+    }
+    for (int k = 0; k < 2; ++k) {
+        if (g->h_in[k]) cudaFreeHost(g->h_in[k]);
+        if (g->h_out[k]) cudaFreeHost(g->h_out[k]);
+        cudaFree(g->d_in[k]); cudaFree(g->d_out[k]); cudaFree(g->d_rows[k]);
+        if (g->ev_k0[k]) cudaEventDestroy(g->ev_k0[k]);
+        if (g->ev_k1[k]) cudaEventDestroy(g->ev_k1[k]);
+        if (g->ev_done[k]) cudaEventDestroy(g->ev_done[k]);
+        if (g->st[k]) cudaStreamDestroy(g->st[k]);
+    }
+    cudaFree(g->d_scratch); cudaFree(g->d_result4);
+    cudaFree(g->owned);
+    delete g;
+    return 0;
+}
+
+// ---- point list ----------------------------------------------------------------------------------
+
+int auvi_interp_points_device(auvi_grid* g, int method, const void* dev_pts, int64_t n,
+                              int64_t stride_bytes, double* dev_out_elev,
+                              int32_t* dev_sel, int32_t* dev_found, void* stream) {
+    if (check_common(g, method)) return 1;
+    if (n < 0) return fail("negative point count");
+    if (n == 0) return 0;
+    if (!dev_pts || !dev_out_elev) return fail("null device buffer");
+    if (stride_bytes < 16 || stride_bytes % 8) return fail("stride_bytes must be a multiple of 8 and >= 16");
+    if ((dev_sel == nullptr) != (dev_found == nullptr)) return fail("dev_sel and dev_found go together");
+    if (g->d.row0 != 0 || g->d.rows != g->d.n_lat) return fail("point-list mode needs the whole grid resident");
+    AUVI_CUDA(cudaSetDevice(g->device));
+    cudaError_t e = launch_points(g->d, method, static_cast<const double*>(dev_pts), stride_bytes / 8, n,
+                                  dev_out_elev, dev_sel, dev_found, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda("point-list launch", e);
+    g_launches.fetch_add(1);
+    return 0;
+}
+
+int auvi_interp_points(auvi_grid* g, int method, const void* host_pts, int64_t n,
+                       int64_t stride_bytes, void* host_out, int64_t out_stride_bytes) {
+    if (check_common(g, method)) return 1;
+    if (n < 0) return fail("negative point count");
+    if (n == 0) return 0;                                        // GridD.cu:96-98: nothing to do
+    if (!host_pts || !host_out) return fail("null host buffer");
+    if (stride_bytes < 16 || stride_bytes % 8) return fail("stride_bytes must be a multiple of 8 and >= 16");
+    if (out_stride_bytes < 8 || out_stride_bytes % 8) return fail("out_stride_bytes must be a multiple of 8");
+    if (g->d.row0 != 0 || g->d.rows != g->d.n_lat) return fail("point-list mode needs the whole grid resident");
+    AUVI_CUDA(cudaSetDevice(g->device));
+    if (ensure_point_staging(g)) return 2;
+
+    const int64_t sd = stride_bytes / 8, od = out_stride_bytes / 8;
+    const double* src = static_cast<const double*>(host_pts);
+    double* dst = static_cast<double*>(host_out);
+    const int64_t n_chunks = (n + kPointChunk - 1) / kPointChunk;
+    float ms_total = 0.f;
+    auto drain = [&](int64_t c) -> int {                         // chunk c: wait, unpack, account
+        const int b = static_cast<int>(c & 1);
+        const int64_t lo = c * kPointChunk, cnt = (n - lo < kPointChunk) ? n - lo : kPointChunk;
+        AUVI_CUDA(cudaEventSynchronize(g->ev_done[b]));
+        const double* r = g->h_out[b];
+        if (od == 1) std::memcpy(dst + lo, r, sizeof(double) * cnt);
+        else for (int64_t k = 0; k < cnt; ++k) dst[(lo + k) * od] = r[k];
+        float ms = 0.f;
+        AUVI_CUDA(cudaEventElapsedTime(&ms, g->ev_k0[b], g->ev_k1[b]));
+        ms_total += ms;
+        return 0;
+    };
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const int b = static_cast<int>(c & 1);
+        const int64_t lo = c * kPointChunk, cnt = (n - lo < kPointChunk) ? n - lo : kPointChunk;
+        if (c >= 2 && drain(c - 2)) return 2;                     // buffer b is free again after this
+        double* pin = g->h_in[b];
+        const double* s = src + lo * sd;
+        for (int64_t k = 0; k < cnt; ++k) { pin[2 * k] = s[k * sd]; pin[2 * k + 1] = s[k * sd + 1]; }
+        cudaStream_t st = g->st[b];
+        AUVI_CUDA(cudaMemcpyAsync(g->d_in[b], pin, sizeof(double) * 2 * cnt, cudaMemcpyHostToDevice, st));
+        AUVI_CUDA(cudaEventRecord(g->ev_k0[b], st));
+        cudaError_t e = launch_points(g->d, method, g->d_in[b], 2, cnt, g->d_out[b], nullptr, nullptr, st);
+        if (e != cudaSuccess) return fail_cuda("point-list launch", e);
+        g_launches.fetch_add(1);
+        AUVI_CUDA(cudaEventRecord(g->ev_k1[b], st));
+        AUVI_CUDA(cudaMemcpyAsync(g->h_out[b], g->d_out[b], sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+        AUVI_CUDA(cudaEventRecord(g->ev_done[b], st));
+    }
+    for (int64_t c = (n_chunks >= 2 ? n_chunks - 2 : 0); c < n_chunks; ++c)
+        if (drain(c)) return 2;
+    g->last_ms = ms_total;
+    return 0;
+}
+
+// ---- lattice ---------------------------------------------------------------------------------------
+
+int auvi_lattice_dims(const auvi_grid* g, int axis_kind, int f_lat, int f_lon, int64_t* out_rows, int64_t* out_cols) {
+    if (!g) return fail("null grid handle");
+    if (axis_kind != AUVI_AXIS_EXPANDED && axis_kind != AUVI_AXIS_NODES) return fail("unknown axis kind");
+    if (f_lat < 1 || f_lon < 1) return fail("lattice factor must be >= 1");
+    if (axis_kind == AUVI_AXIS_NODES && (f_lat != 1 || f_lon != 1)) return fail("AUVI_AXIS_NODES requires factor 1");
+    if (out_rows) *out_rows = static_cast<int64_t>(f_lat) * (g->d.n_lat - 1) + 1;
+    if (out_cols) *out_cols = static_cast<int64_t>(f_lon) * (g->d.n_lon - 1) + 1;
+    return 0;
+}
+
+int auvi_lattice_device(auvi_grid* g, int method, int axis_kind, int f_lat, int f_lon, int fill,
+                        int64_t row_begin, int64_t row_end, void* dev_out, int64_t out_ld,
+                        int32_t* dev_sel9, void* stream) {
+    if (check_common(g, method)) return 1;
+    int64_t rows = 0, cols = 0;
+    if (auvi_lattice_dims(g, axis_kind, f_lat, f_lon, &rows, &cols)) return 1;
+    if (fill && (axis_kind != AUVI_AXIS_NODES)) return fail("fill mode requires AUVI_AXIS_NODES");
+    if (row_begin < 0 || row_end > rows || row_begin > row_end) return fail("row range outside the lattice");
+    if (row_begin == row_end) return 0;
+    if (!dev_out) return fail("null device output");
+    if (out_ld < cols) return fail("out_ld must be >= lattice columns");
+    AUVI_CUDA(cudaSetDevice(g->device));
+    AxisOwned *lat = nullptr, *lon = nullptr;
+    if (get_axis(g, 1, axis_kind, f_lat, &lat) || get_axis(g, 0, axis_kind, f_lon, &lon)) return 1;
+    LaunchInfo info;
+    cudaError_t e = launch_lattice(g->d, method, lat->view(), lon->view(), row_begin, row_end, dev_out, out_ld,
+                                   fill, dev_sel9, static_cast<cudaStream_t>(stream), &info);
+    if (e == cudaErrorInvalidValue && (g->d.row0 != 0 || g->d.rows != g->d.n_lat))
+        return fail("row range needs grid rows outside the resident slab (halo too small)");
+    if (e != cudaSuccess) return fail_cuda("lattice launch", e);
+    g_launches.fetch_add(info.launches);
+    g->last_tma = info.used_tma;
+    return 0;
+}
+
+int auvi_lattice(auvi_grid* g, int method, int axis_kind, int f_lat, int f_lon, int fill,
+                 int64_t row_begin, int64_t row_end, void* host_out) {
+    if (check_common(g, method)) return 1;
+    int64_t rows = 0, cols = 0;
+    if (auvi_lattice_dims(g, axis_kind, f_lat, f_lon, &rows, &cols)) return 1;
+    if (row_begin < 0 || row_end > rows || row_begin > row_end) return fail("row range outside the lattice");
+    if (row_begin == row_end) return 0;
+    if (!host_out) return fail("null host output");
+    AUVI_CUDA(cudaSetDevice(g->device));
+    const size_t es = g->d.dtype == AUVI_F64 ? 8 : 4;
+    const int64_t row_bytes = cols * static_cast<int64_t>(es);
+    int64_t chunk_rows = kLatticeChunkBytes / row_bytes;
+    if (chunk_rows < 1) chunk_rows = 1;
+    if (chunk_rows > row_end - row_begin) chunk_rows = row_end - row_begin;
+    const size_t need = static_cast<size_t>(chunk_rows) * row_bytes;
+    if (need > g->d_rows_bytes) {
+        for (int k = 0; k < 2; ++k) { cudaFree(g->d_rows[k]); g->d_rows[k] = nullptr; }
+        g->d_rows_bytes = 0;
+        for (int k = 0; k < 2; ++k) AUVI_CUDA(cudaMalloc(&g->d_rows[k], need));
+        g->d_rows_bytes = need;
+    }
+    float ms_total = 0.f;
+    int64_t c = 0;
+    for (int64_t r = row_begin; r < row_end; r += chunk_rows, ++c) {
+        const int b = static_cast<int>(c & 1);
+        const int64_t r_hi = (r + chunk_rows < row_end) ? r + chunk_rows : row_end;
+        cudaStream_t st = g->st[b];
+        if (c >= 2) {                                             // staging buffer b: previous copy drained?
+            AUVI_CUDA(cudaEventSynchronize(g->ev_done[b]));
+            float ms = 0.f;
+            AUVI_CUDA(cudaEventElapsedTime(&ms, g->ev_k0[b], g->ev_k1[b]));
+            ms_total += ms;
+        }
+        AUVI_CUDA(cudaEventRecord(g->ev_k0[b], st));
+        if (auvi_lattice_device(g, method, axis_kind, f_lat, f_lon, fill, r, r_hi, g->d_rows[b], cols, nullptr, st))
+            return 2;
+        AUVI_CUDA(cudaEventRecord(g->ev_k1[b], st));
+        AUVI_CUDA(cudaMemcpyAsync(static_cast<char*>(host_out) + (r - row_begin) * row_bytes, g->d_rows[b],
+                                  static_cast<size_t>(r_hi - r) * row_bytes, cudaMemcpyDeviceToHost, st));
+        AUVI_CUDA(cudaEventRecord(g->ev_done[b], st));
+    }
+    for (int64_t k = (c >= 2 ? c - 2 : 0); k < c; ++k) {
+        const int b = static_cast<int>(k & 1);
+        AUVI_CUDA(cudaEventSynchronize(g->ev_done[b]));
+        float ms = 0.f;
+        AUVI_CUDA(cudaEventElapsedTime(&ms, g->ev_k0[b], g->ev_k1[b]));
+        ms_total += ms;
+    }
+    g->last_ms = ms_total;
+    return 0;
+}
+
+// ---- metrics ---------------------------------------------------------------------------------------
+
+int auvi_error_metrics_device(const void* dev_truth, const void* dev_est, int dtype, int64_t n,
+                              double* out3, int64_t* out_nan, void* stream) {
+    if (dtype != AUVI_F64 && dtype != AUVI_F32) return fail("dtype must be AUVI_F64 or AUVI_F32");
+    if (n <= 0) return fail("Error: Reference or interpolated points vector is empty or sizes do not match.");
+    if (!dev_truth || !dev_est || !out3) return fail("null buffer");
+    if (auvi_device_count() <= 0) return fail("no CUDA device: libauvi has no CPU fallback");
+    void* scratch = nullptr;
+    double* result4 = nullptr;
+    AUVI_CUDA(cudaMalloc(&scratch, metrics_scratch_bytes()));
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&result4), sizeof(double) * 4);
+    if (e != cudaSuccess) { cudaFree(scratch); return fail_cuda("cudaMalloc", e); }
+    LaunchInfo info;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    e = launch_metrics(dev_truth, dev_est, dtype, n, scratch, result4, st, &info);
+    double h[4] = {0, 0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, result4, sizeof h, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(scratch); cudaFree(result4);
+    if (e != cudaSuccess) return fail_cuda("metrics", e);
+    g_launches.fetch_add(info.launches);
+    out3[0] = h[0] / static_cast<double>(n);                       // error_calculator.cpp:17
+    out3[1] = std::sqrt(h[1] / static_cast<double>(n));            // :32
+    out3[2] = h[2];
+    if (out_nan) *out_nan = static_cast<int64_t>(h[3]);
+    return 0;
+}
+
+}  // extern "C"

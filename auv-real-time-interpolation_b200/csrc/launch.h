@@ -50,13 +50,24 @@ struct AxisTables {
 cudaError_t launch_points(const GridDesc& d, int method, const double* pts, int64_t stride_dbl, int64_t n,
                           double* out, int32_t* sel, int32_t* found, cudaStream_t st);
 
+// What a lattice launch did (diagnostics surfaced through the C-ABI).
+struct LaunchInfo {
+    int launches = 0;              // kernels launched
+    int used_tma = 0;              // 1 if the input tiles were staged by TMA
+};
+
 // upsample.cu -- lattice mode: out[(J-row_begin)*out_ld + I] for J in [row_begin,row_end), all I.
 // fill != 0: cells whose own grid value is valid are passed through (Grid-B gap fill on AXIS_NODES).
-// tmap may be null (no TMA: row pitch not a multiple of 16 B); sel (optional) is n x 8 int32.
+// sel (optional) is 9 int32 per output cell: {found, i0,j0,...,i3,j3}.
 cudaError_t launch_lattice(const GridDesc& d, int method, const AxisTables& lat, const AxisTables& lon,
                            int64_t row_begin, int64_t row_end, void* out, int64_t out_ld,
-                           int fill, int32_t* sel, const CUtensorMap* tmap_template,
-                           cudaStream_t st, int* launches);
+                           int fill, int32_t* sel, cudaStream_t st, LaunchInfo* info);
+
+// metrics.cu -- MAE / RMSE / Max / NaN count of est against truth (error_calculator.cpp:5-45).
+// scratch: device buffer of metrics_scratch_bytes(); result4 (device): {sum|d|, sum d^2, max|d|, #NaN}.
+size_t metrics_scratch_bytes();
+cudaError_t launch_metrics(const void* truth, const void* est, int dtype, int64_t n, void* scratch,
+                           double* result4, cudaStream_t st, LaunchInfo* info);
 
 // Encodes a 2-D tiled tensor map over the grid slab; returns false when TMA cannot address it.
 bool make_grid_tensor_map(const GridDesc& d, int box_w, int box_h, CUtensorMap* out);

@@ -20,7 +20,7 @@ points_kernel(GridView<T> g, const double* __restrict__ pts, int64_t stride_dbl,
               double* __restrict__ out, int32_t* __restrict__ sel, int32_t* __restrict__ found) {
     __shared__ double s_lonlat[kPointsBlock * 2];
     const int64_t base = static_cast<int64_t>(blockIdx.x) * kPointsBlock;
-    const int live = static_cast<int>(min<int64_t>(kPointsBlock, n - base));
+    const int live = static_cast<int>(min(static_cast<int64_t>(kPointsBlock), n - base));
 
     if (stride_dbl == 3) {
         // 256 records = 768 contiguous doubles; keep lon,lat (2 of every 3).

@@ -86,7 +86,7 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const TileParams
     const int W = p.lon.n;
     const int I0 = blockIdx.x * kTileCols;
     const int64_t J0 = p.row_begin + static_cast<int64_t>(blockIdx.y) * p.tj;
-    const int nJ = static_cast<int>(min<int64_t>(p.tj, p.row_end - J0));
+    const int nJ = static_cast<int>(min(static_cast<int64_t>(p.tj), p.row_end - J0));
     const int c0 = __ldg(p.lon.base + I0) - LO;                    // global column of tile column 0
     const int r0 = __ldg(p.lat.base + J0) - LO;                    // global row of tile row 0
     const int bw = p.bw, bh = p.bh;
@@ -286,7 +286,7 @@ static int max_span(const int* h_base, int64_t begin, int64_t end, int tile, int
 
 template <typename T, int METHOD>
 static cudaError_t launch_tiled(const GridDesc& d, const AxisTables& lat, const AxisTables& lon, int64_t row_begin,
-                                int64_t row_end, void* out, int64_t out_ld, cudaStream_t st) {
+                                int64_t row_end, void* out, int64_t out_ld, cudaStream_t st, LaunchInfo* info) {
     const int taps = METHOD == CUBIC ? 4 : 2;
     const int lo = METHOD == CUBIC ? 1 : 0;
     const size_t es = sizeof(T);
@@ -299,8 +299,10 @@ static cudaError_t launch_tiled(const GridDesc& d, const AxisTables& lat, const 
         tj /= 2;
         bh = max_span(lat.h_base, row_begin, row_end, tj, taps);
     }
-    // slab check: every input row a tile touches (after the reference's clamp) must be resident
-    int need_lo = lat.h_base[row_begin] - lo, need_hi = lat.h_base[row_end - 1] - lo + taps - 1;
+    // slab check: every input row a tile touches (after the reference's clamp) must be resident;
+    // bicubic outputs with a NaN in their footprint fall back to the radius-10 ring search.
+    const int reach = METHOD == CUBIC ? kMaxRadius + 1 : 0;
+    int need_lo = lat.h_base[row_begin] - lo - reach, need_hi = lat.h_base[row_end - 1] - lo + taps - 1 + reach;
     need_lo = need_lo < 0 ? 0 : need_lo;
     need_hi = need_hi > d.n_lat - 1 ? d.n_lat - 1 : need_hi;
     if (need_lo < d.row0 || need_hi >= d.row0 + d.rows) return cudaErrorInvalidValue;
@@ -314,9 +316,10 @@ static cudaError_t launch_tiled(const GridDesc& d, const AxisTables& lat, const 
     p.tj = tj; p.bw = bw; p.bh = bh;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
-    // TMA needs the whole slab to be exactly the tensor (rows outside the slab but inside the grid
-    // would be zero-filled silently), so it is only used when the slab is the full grid.
-    p.use_tma = (d.row0 == 0 && d.rows == d.n_lat && make_grid_tensor_map(d, bw, bh, &tmap)) ? 1 : 0;
+    // The tensor map covers the resident slab; box rows outside it are zero-filled.  The slab check
+    // above guarantees that every row a tile actually reads is resident, and rows outside the GLOBAL
+    // grid are patched to the clamped edge row inside the kernel.
+    p.use_tma = make_grid_tensor_map(d, bw, bh, &tmap) ? 1 : 0;
 
     const size_t smem = static_cast<size_t>(bw) * bh * es;
     auto kern = upsample_tiled_kernel<T, METHOD>;
@@ -327,12 +330,20 @@ static cudaError_t launch_tiled(const GridDesc& d, const AxisTables& lat, const 
     dim3 grid(static_cast<unsigned>((lon.n + kTileCols - 1) / kTileCols),
               static_cast<unsigned>((row_end - row_begin + tj - 1) / tj));
     kern<<<grid, kTileCols, smem, st>>>(tmap, p);
+    if (info) { info->launches += 1; info->used_tma = p.use_tma; }
     return cudaGetLastError();
 }
 
 template <typename T, int METHOD, bool FILL>
 static cudaError_t launch_exact(const GridDesc& d, const AxisTables& lat, const AxisTables& lon, int64_t row_begin,
-                                int64_t row_end, void* out, int64_t out_ld, int32_t* sel, cudaStream_t st) {
+                                int64_t row_end, void* out, int64_t out_ld, int32_t* sel, cudaStream_t st,
+                                LaunchInfo* info) {
+    // every row the ring search (radius 10 around a floor/round centre) may read must be resident
+    int need_lo = lat.h_base[row_begin] - (kMaxRadius + 1), need_hi = lat.h_base[row_end - 1] + (kMaxRadius + 2);
+    need_lo = need_lo < 0 ? 0 : need_lo;
+    need_hi = need_hi > d.n_lat - 1 ? d.n_lat - 1 : need_hi;
+    if (need_lo < d.row0 || need_hi >= d.row0 + d.rows) return cudaErrorInvalidValue;
+    if (info) { info->launches += 1; info->used_tma = 0; }
     const int64_t total = (row_end - row_begin) * lon.n;
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 64) blocks = 148 * 64;
@@ -345,15 +356,15 @@ static cudaError_t launch_exact(const GridDesc& d, const AxisTables& lat, const 
 template <typename T>
 static cudaError_t launch_lattice_t(const GridDesc& d, int method, const AxisTables& lat, const AxisTables& lon,
                                     int64_t row_begin, int64_t row_end, void* out, int64_t out_ld, int fill,
-                                    int32_t* sel, cudaStream_t st) {
+                                    int32_t* sel, cudaStream_t st, LaunchInfo* info) {
     if (!fill && !sel) {
-        if (method == BILINEAR) return launch_tiled<T, BILINEAR>(d, lat, lon, row_begin, row_end, out, out_ld, st);
-        if (method == CUBIC) return launch_tiled<T, CUBIC>(d, lat, lon, row_begin, row_end, out, out_ld, st);
+        if (method == BILINEAR) return launch_tiled<T, BILINEAR>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
+        if (method == CUBIC) return launch_tiled<T, CUBIC>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
     }
 #define AUVI_CASE(M)                                                                                         \
     case M:                                                                                                  \
-        return fill ? launch_exact<T, M, true>(d, lat, lon, row_begin, row_end, out, out_ld, sel, st)        \
-                    : launch_exact<T, M, false>(d, lat, lon, row_begin, row_end, out, out_ld, sel, st);
+        return fill ? launch_exact<T, M, true>(d, lat, lon, row_begin, row_end, out, out_ld, sel, st, info)  \
+                    : launch_exact<T, M, false>(d, lat, lon, row_begin, row_end, out, out_ld, sel, st, info);
     switch (method) {
         AUVI_CASE(BILINEAR) AUVI_CASE(CUBIC) AUVI_CASE(KRIGING) AUVI_CASE(NN) AUVI_CASE(IDW)
         default: return cudaErrorInvalidValue;
@@ -363,12 +374,11 @@ static cudaError_t launch_lattice_t(const GridDesc& d, int method, const AxisTab
 
 cudaError_t launch_lattice(const GridDesc& d, int method, const AxisTables& lat, const AxisTables& lon,
                            int64_t row_begin, int64_t row_end, void* out, int64_t out_ld, int fill, int32_t* sel,
-                           const CUtensorMap*, cudaStream_t st, int* launches) {
+                           cudaStream_t st, LaunchInfo* info) {
     if (row_end <= row_begin) return cudaSuccess;
-    if (launches) *launches += 1;
     if (d.dtype == DT_F64)
-        return launch_lattice_t<double>(d, method, lat, lon, row_begin, row_end, out, out_ld, fill, sel, st);
-    return launch_lattice_t<float>(d, method, lat, lon, row_begin, row_end, out, out_ld, fill, sel, st);
+        return launch_lattice_t<double>(d, method, lat, lon, row_begin, row_end, out, out_ld, fill, sel, st, info);
+    return launch_lattice_t<float>(d, method, lat, lon, row_begin, row_end, out, out_ld, fill, sel, st, info);
 }
 
 }  // namespace auvi

@@ -1,0 +1,177 @@
+"""ctypes view of libauvi.so (include/auvi.h) for tests, bench.py and __graft_entry__.py.
+
+This is plumbing, not product: the product is the C-ABI library and the C++ class GridD on top of
+it (host/GridD.cpp).  Nothing here computes; every call goes to the CUDA library, and loading
+fails loudly when the library is missing -- there is no CPU fallback (tests/test_abi_cpu.py checks
+that this module never imports anything from oracle/).
+
+    g = auvi.Grid(z, min_lon, max_lon, min_lat, max_lat)          # uploads, like GridD::GridD
+    out = g.interp_points(auvi.KRIGING, pts)                        # host Point list -> host depths
+    lat = g.lattice(auvi.CUBIC, auvi.AXIS_EXPANDED, 2, 2)           # (2n-1)x(2n-1) host array
+    g.lattice_device(...), g.interp_points_device(...)              # raw device pointers (torch .data_ptr())
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+LIB_PATH = os.path.join(PKG, "lib", "libauvi.so")
+
+BILINEAR, CUBIC, KRIGING, NN, IDW = 0, 1, 2, 3, 4
+METHOD_NAMES = {BILINEAR: "bilinear", CUBIC: "cubic", KRIGING: "kriging", NN: "nn", IDW: "idw"}
+F64, F32 = 0, 1
+AXIS_EXPANDED, AXIS_NODES = 0, 1
+
+# every symbol include/auvi.h declares: (name, restype, argtypes)
+_vp, _i64, _i32, _dbl = C.c_void_p, C.c_int64, C.c_int, C.c_double
+SYMBOLS = {
+    "auvi_grid_create": (_i32, [_vp, _i32, _i64, _i64, _dbl, _dbl, _dbl, _dbl, _i32, C.POINTER(_vp)]),
+    "auvi_grid_adopt": (_i32, [_vp, _i32, _i64, _i64, _i64, _i64, _i64, _dbl, _dbl, _dbl, _dbl, _i32, C.POINTER(_vp)]),
+    "auvi_grid_destroy": (_i32, [_vp]),
+    "auvi_interp_points": (_i32, [_vp, _i32, _vp, _i64, _i64, _vp, _i64]),
+    "auvi_interp_points_device": (_i32, [_vp, _i32, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "auvi_lattice_dims": (_i32, [_vp, _i32, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64)]),
+    "auvi_lattice_device": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "auvi_lattice": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _vp]),
+    "auvi_error_metrics_device": (_i32, [_vp, _vp, _i32, _i64, C.POINTER(_dbl), C.POINTER(_i64), _vp]),
+    "auvi_last_error": (C.c_char_p, []),
+    "auvi_last_kernel_ms": (C.c_float, [_vp]),
+    "auvi_launch_count": (_i64, []),
+    "auvi_uses_tma": (_i32, [_vp]),
+    "auvi_device_count": (_i32, []),
+    "auvi_version": (_i32, []),
+}
+
+_lib = None
+
+
+class AuviError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libauvi.so and bind every declared symbol.  Raises if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AuviError(f"{LIB_PATH} is missing: build it (python -c 'import __graft_entry__ as g; g.build()'); "
+                        "there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the export is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise AuviError(load().auvi_last_error().decode())
+
+
+def launch_count() -> int:
+    return int(load().auvi_launch_count())
+
+
+def device_count() -> int:
+    return int(load().auvi_device_count())
+
+
+def _np_dtype(dtype):
+    return np.float64 if dtype == F64 else np.float32
+
+
+class Grid:
+    """A depth grid resident on one GPU (handle owner)."""
+
+    def __init__(self, z=None, min_lon=0.0, max_lon=0.0, min_lat=0.0, max_lat=0.0, device=0, dtype=None,
+                 adopt=None):
+        lib = load()
+        self._h = _vp()
+        self.bounds = (min_lon, max_lon, min_lat, max_lat)
+        if adopt is not None:
+            # adopt = dict(ptr, dtype, n_lat, n_lon, ld, row0, rows): borrow device memory (e.g. a torch tensor)
+            self.dtype = adopt["dtype"]
+            self.n_lat, self.n_lon = adopt["n_lat"], adopt["n_lon"]
+            _check(lib.auvi_grid_adopt(adopt["ptr"], self.dtype, self.n_lat, self.n_lon, adopt["ld"], adopt["row0"],
+                                       adopt["rows"], min_lon, max_lon, min_lat, max_lat, device, C.byref(self._h)))
+            self._keep = adopt.get("keep")
+        else:
+            if dtype is None:
+                dtype = F32 if np.asarray(z).dtype == np.float32 else F64
+            self.dtype = dtype
+            z = np.ascontiguousarray(z, dtype=_np_dtype(dtype))
+            self.n_lat, self.n_lon = z.shape
+            _check(lib.auvi_grid_create(z.ctypes.data, dtype, self.n_lat, self.n_lon, min_lon, max_lon, min_lat,
+                                        max_lat, device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            load().auvi_grid_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- point list ------------------------------------------------------------------------------
+    def interp_points(self, method, pts):
+        """pts: n x 3 float64 {lon,lat,elev} (Point.h:9-13) on the host -> n float64 depths."""
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        assert pts.ndim == 2 and pts.shape[1] >= 2
+        out = np.empty(pts.shape[0], dtype=np.float64)
+        _check(load().auvi_interp_points(self._h, method, pts.ctypes.data, pts.shape[0], pts.strides[0],
+                                         out.ctypes.data, 8))
+        return out
+
+    def interp_points_device(self, method, pts_ptr, n, stride_bytes, out_ptr, sel_ptr=None, found_ptr=None, stream=None):
+        _check(load().auvi_interp_points_device(self._h, method, pts_ptr, n, stride_bytes, out_ptr, sel_ptr,
+                                                found_ptr, stream))
+
+    # ---- lattice ---------------------------------------------------------------------------------
+    def lattice_dims(self, axis_kind, f_lat=1, f_lon=1):
+        r, c = _i64(), _i64()
+        _check(load().auvi_lattice_dims(self._h, axis_kind, f_lat, f_lon, C.byref(r), C.byref(c)))
+        return r.value, c.value
+
+    def lattice(self, method, axis_kind, f_lat=1, f_lon=1, fill=0, row_begin=0, row_end=None, out=None):
+        rows, cols = self.lattice_dims(axis_kind, f_lat, f_lon)
+        if row_end is None:
+            row_end = rows
+        if out is None:
+            out = np.empty((row_end - row_begin, cols), dtype=_np_dtype(self.dtype))
+        _check(load().auvi_lattice(self._h, method, axis_kind, f_lat, f_lon, fill, row_begin, row_end, out.ctypes.data))
+        return out
+
+    def lattice_into(self, method, axis_kind, f_lat, f_lon, fill, row_begin, row_end, host_ptr):
+        _check(load().auvi_lattice(self._h, method, axis_kind, f_lat, f_lon, fill, row_begin, row_end, host_ptr))
+
+    def lattice_device(self, method, axis_kind, f_lat, f_lon, fill, row_begin, row_end, out_ptr, out_ld,
+                       sel9_ptr=None, stream=None):
+        _check(load().auvi_lattice_device(self._h, method, axis_kind, f_lat, f_lon, fill, row_begin, row_end,
+                                          out_ptr, out_ld, sel9_ptr, stream))
+
+    # ---- diagnostics -----------------------------------------------------------------------------
+    @property
+    def last_kernel_ms(self):
+        return float(load().auvi_last_kernel_ms(self._h))
+
+    @property
+    def uses_tma(self):
+        return bool(load().auvi_uses_tma(self._h))
+
+
+def error_metrics_device(truth_ptr, est_ptr, dtype, n, stream=None):
+    """-> (mae, rmse, max, n_nan) with the reference's NaN convention (error_calculator.cpp:5-45)."""
+    out3 = (_dbl * 3)()
+    nn = _i64()
+    _check(load().auvi_error_metrics_device(truth_ptr, est_ptr, dtype, n, out3, C.byref(nn), stream))
+    return out3[0], out3[1], out3[2], nn.value

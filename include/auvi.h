@@ -2,11 +2,11 @@
  * devsaxena974/AUV-Real-Time-Interpolation (code/src/GridD.cu + code/src/kernels.cu).
  *
  * Everything the reference's host code needs from the device goes through these entry points:
- * plain pointers and sizes, no C++/torch types.  include/GridD.h is the C++ class with the
- * reference's own signatures written on top of it; INTEGRATION.md shows the binding a maintainer
- * of the reference would add.  All functions return 0 on success, non-zero on failure with a
- * message available from auvi_last_error().  There is no CPU fallback: without a CUDA device every
- * compute call fails.
+ * plain pointers and sizes, no C++/torch types.  The C++ class `GridD` with the reference's own
+ * signatures (auv-real-time-interpolation_b200/host/GridD.{h,cpp}) is written on top of it;
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.  All functions return
+ * 0 on success, non-zero on failure with a message available from auvi_last_error().  There is no
+ * CPU fallback: without a CUDA device every compute call fails.
  *
  * Reference citations are file:line in /root/reference/code.
  */
@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-typedef struct auvi_grid auvi_grid;   /* opaque: a depth grid resident on one GPU */
+typedef struct auvi_grid auvi_grid;   /* opaque: a depth grid (or a row slab of one) resident on one GPU */
 
 /* Interpolation methods.  0-2 are the reference's three (include/GridD.h:69,77,85);
  * 3-4 are extensions defined on the reference's own neighbour search. */
@@ -53,11 +53,13 @@ int auvi_grid_destroy(auvi_grid* g);      /* idempotent on NULL */
 /* ---- Point-list mode: replaces GridD::batch{Bilinear,Cubic,OrdinaryKriging}Interpolate
  *      (src/GridD.cu:95-150,156-193,199-236) and the three kernels of src/kernels.cu:173-546 ---- */
 
-/* host_pts: n records of `stride_bytes` (24 for struct Point{lon,lat,elev}, include/Point.h:9-13);
- * host_out_elev[n] receives the interpolated depth (NaN outside the bounds, kernels.cu:193-196).
- * Synchronous; persistent pinned staging + device buffers are reused across calls. */
+/* host_pts: n records of `stride_bytes` whose first two doubles are lon,lat (24 for struct
+ * Point{lon,lat,elev}, include/Point.h:9-13).  The interpolated depth of record k is written to
+ * (char*)host_out + k*out_stride_bytes (8 for a dense double array, 24 to fill Point::elev in
+ * place); NaN outside the bounds (kernels.cu:193-196).  Synchronous.  Pinned staging and device
+ * buffers persist across calls; copies and kernels of successive chunks overlap. */
 int auvi_interp_points(auvi_grid* g, int method, const void* host_pts, int64_t n,
-                       int64_t stride_bytes, double* host_out_elev);
+                       int64_t stride_bytes, void* host_out, int64_t out_stride_bytes);
 
 /* Same on device-resident buffers, asynchronous on `stream` (a cudaStream_t, may be NULL).
  * dev_sel (optional, n x 8 int32) / dev_found (optional, n int32) receive the neighbour selection
@@ -79,27 +81,30 @@ int auvi_lattice_dims(const auvi_grid* g, int axis_kind, int f_lat, int f_lon,
 
 /* Upsample (fill = 0) or gap-fill (fill = 1: cells whose own value is valid are copied through,
  * NaN cells get method(query at that node); requires axis kind NODES and factors 1).
- * dev_out: (row_end-row_begin) rows of out_ld elements of the grid's dtype.  Asynchronous on stream. */
+ * dev_out: (row_end-row_begin) rows of out_ld elements of the grid's dtype.  dev_sel9 (optional):
+ * per output cell {found, i0,j0,...,i3,j3} int32.  Asynchronous on stream. */
 int auvi_lattice_device(auvi_grid* g, int method, int axis_kind, int f_lat, int f_lon, int fill,
                         int64_t row_begin, int64_t row_end, void* dev_out, int64_t out_ld,
                         int32_t* dev_sel9, void* stream);
 
 /* Host-buffer form: result rows are copied to host_out (dense, out_cols elements per row) inside
- * the call; synchronous. */
+ * the call, row chunks double-buffered so that kernels overlap the device->host copies;
+ * synchronous. */
 int auvi_lattice(auvi_grid* g, int method, int axis_kind, int f_lat, int f_lon, int fill,
                  int64_t row_begin, int64_t row_end, void* host_out);
 
 /* ---- Error metrics on device: replaces meanAbsoluteError / rootMeanSquareError /
  *      maxAbsoluteError (src/error_calculator.cpp:5-45), same NaN/denominator convention.
- *      out3 = {MAE, RMSE, Max}; out_nan = number of NaN estimates. */
+ *      out3 = {MAE, RMSE, Max}; out_nan = number of NaN estimates.  Synchronous on `stream`. */
 int auvi_error_metrics_device(const void* dev_truth, const void* dev_est, int dtype, int64_t n,
                               double* out3, int64_t* out_nan, void* stream);
 
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 const char* auvi_last_error(void);          /* thread-local message of the last failure */
-float auvi_last_kernel_ms(const auvi_grid* g); /* device time of the last synchronous call's kernels */
+float auvi_last_kernel_ms(const auvi_grid* g); /* device time of the kernels of the last synchronous call */
 int64_t auvi_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 int auvi_uses_tma(const auvi_grid* g);      /* 1 if the last lattice launch staged tiles by TMA */
+int auvi_device_count(void);                /* CUDA devices visible (0 when none: compute calls fail) */
 int auvi_version(void);
 
 #ifdef __cplusplus
