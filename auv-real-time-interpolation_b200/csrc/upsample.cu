@@ -26,6 +26,9 @@
 //     exact path; with FILL it passes valid cells through untouched.
 //
 // Algorithmic HBM bytes per output cell: s_out + s_in/(f_lat*f_lon).
+#include <cstdlib>
+#include <cstring>
+
 #include "exact.cuh"
 #include "launch.h"
 #include "tma.cuh"
@@ -87,7 +90,11 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const TileParams
     const int I0 = blockIdx.x * kTileCols;
     const int64_t J0 = p.row_begin + static_cast<int64_t>(blockIdx.y) * p.tj;
     const int nJ = static_cast<int>(min(static_cast<int64_t>(p.tj), p.row_end - J0));
-    const int c0 = __ldg(p.lon.base + I0) - LO;                    // global column of tile column 0
+    // global column of tile column 0, rounded down to a 16-byte boundary: with no swizzle/interleave
+    // the TMA unit faults ("illegal instruction") on a box whose first element is not 16-byte aligned
+    // in global memory (measured on B200: profiles/r01_tma_alignment_probe.txt)
+    constexpr int kAlign = 16 / static_cast<int>(sizeof(T));
+    const int c0 = (__ldg(p.lon.base + I0) - LO) & ~(kAlign - 1);
     const int r0 = __ldg(p.lat.base + J0) - LO;                    // global row of tile row 0
     const int bw = p.bw, bh = p.bh;
 
@@ -257,6 +264,8 @@ static EncodeTiledFn encode_fn() {
 
 bool make_grid_tensor_map(const GridDesc& d, int box_w, int box_h, CUtensorMap* out) {
     const size_t es = d.dtype == DT_F64 ? 8 : 4;
+    static const bool disabled = getenv("AUVI_NO_TMA") != nullptr;       // debugging / A-B measurements only
+    if (disabled) return false;
     if (box_w > 256 || box_h > 256 || box_w < 1 || box_h < 1) return false;
     if ((d.ld * es) % 16 != 0 || (reinterpret_cast<uintptr_t>(d.z) % 16) != 0) return false;
     if ((box_w * es) % 16 != 0) return false;
@@ -273,12 +282,14 @@ bool make_grid_tensor_map(const GridDesc& d, int box_w, int box_h, CUtensorMap* 
     return r == CUDA_SUCCESS;
 }
 
-// Largest input span (in cells) any tile of `tile` consecutive outputs needs along one axis.
-static int max_span(const int* h_base, int64_t begin, int64_t end, int tile, int taps) {
+// Largest input span (in cells) any tile of `tile` consecutive outputs needs along one axis, when the
+// first cell of a tile is (base - lo) rounded down to a multiple of `align` (a power of two).
+static int max_span(const int* h_base, int64_t begin, int64_t end, int tile, int taps, int lo, int align) {
     int worst = 0;
     for (int64_t a = begin; a < end; a += tile) {
         int64_t b = (a + tile - 1 < end - 1) ? a + tile - 1 : end - 1;
-        int s = h_base[b] - h_base[a] + taps;
+        int first = (h_base[a] - lo) & ~(align - 1);
+        int s = h_base[b] - lo + taps - first;
         if (s > worst) worst = s;
     }
     return worst;
@@ -292,12 +303,12 @@ static cudaError_t launch_tiled(const GridDesc& d, const AxisTables& lat, const 
     const size_t es = sizeof(T);
     const int align = static_cast<int>(16 / es);
     int tj = 64;
-    int bw = max_span(lon.h_base, 0, lon.n, kTileCols, taps);
+    int bw = max_span(lon.h_base, 0, lon.n, kTileCols, taps, lo, align);
     bw = (bw + align - 1) / align * align;
-    int bh = max_span(lat.h_base, row_begin, row_end, tj, taps);
+    int bh = max_span(lat.h_base, row_begin, row_end, tj, taps, lo, 1);
     while (static_cast<size_t>(bw) * bh * es > 96 * 1024 && tj > 8) {       // keep >=2 CTAs/SM of smem
         tj /= 2;
-        bh = max_span(lat.h_base, row_begin, row_end, tj, taps);
+        bh = max_span(lat.h_base, row_begin, row_end, tj, taps, lo, 1);
     }
     // slab check: every input row a tile touches (after the reference's clamp) must be resident;
     // bicubic outputs with a NaN in their footprint fall back to the radius-10 ring search.

@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement (contract in the task statement; DESIGN.md section "Measurement").
+
+Workload (config.workload): BASELINE.json configs[3] -- a synthetic 16384 x 16384 FP32 depth grid
+(the seamount field of the reference's generate_csv_grids.cpp:32-70), upsampled 4x in both axes with
+the bicubic Catmull-Rom stencil -> 65533 x 65533 output cells per GPU.  It is the largest
+single-GPU configuration of BASELINE.json and the one its roofline is quoted on (HBM-bound).
+N > 1: weak scaling -- the global grid is (16384*N) x 16384, output rows are sharded across ranks,
+each rank holds its input row slab + halo; no data-path collective (DESIGN.md "Multi-GPU").
+
+One JSON line on rank 0:
+  value       output Mcells/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e         same metric through the host-buffer C-ABI call (auvi_grid_create + auvi_lattice):
+              host->device copy of the grid and device->host copy of every output cell inside the timed region
+  roofline    dominant kernel (upsample_tiled_kernel<float,CUBIC>): algorithmic bytes / event time vs
+              the measured copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the reference's own CPU class (oracle/_ref, GridH::batchCubicInterpolate) on a bounded
+              row block of the same lattice, all host threads
+  extra       the other methods / BASELINE configs (bilinear upsample, gap-fill methods on a 70 % masked
+              grid, Mariana 50 % through the Point-list API with RMSE) -- informational
+`--impl reference` times only the reference CPU implementation on the same config and metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "auv-real-time-interpolation_b200", "python"))
+sys.path.insert(0, ROOT)
+
+N_GRID = 16384
+FACTOR = 4
+BOUNDS = (-180.0, -160.0, 20.0, 30.0)          # test_interpolation.cpp:143-144
+ALGO_BYTES_PER_CELL = 4.0 + 4.0 / (FACTOR * FACTOR)   # f32 out + f32 in / 16
+CPU_SAMPLE_ROWS = 256                           # lattice rows timed on the CPU (x 65533 columns)
+METRIC = "output Mcells/s (bicubic 4x upsample, 16384^2 f32 -> 65533^2)"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get("upsample_cubic_f32_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_grid_device(torch, n_lat_global, n_lon, row_lo, row_hi, device):
+    """Rows [row_lo,row_hi) of the seamount field (generate_csv_grids.cpp:32-70) in FP32, on device."""
+    i = torch.arange(n_lon, device=device, dtype=torch.float64) * (100.0 / (n_lon - 1))
+    j = torch.arange(row_lo, row_hi, device=device, dtype=torch.float64) * (100.0 / (n_lat_global - 1))
+    z = -(10.0 + 2.0 * i)[None, :] + 100.0 * torch.exp(-(((i - 75.0) ** 2)[None, :] + ((j - 50.0) ** 2)[:, None]) / 450.0)
+    return z.to(torch.float32).contiguous()
+
+
+def cpu_reference_rate(sample_rows, threads, steps=1, warmup=0, method=1):
+    """Reference CPU path (oracle/_ref GridH, else the C port) on `sample_rows` rows of the workload's
+    output lattice.  -> (Mcells/s, kind, cores, ms per step, sample description)"""
+    from oracle import binding as ob
+    n = N_GRID
+    z = ob.synth_grid(n, n, csv_round=False).astype(np.float32).astype(np.float64)
+    rows_out = FACTOR * (n - 1) + 1
+    lat_ax = ob.lattice_axis(BOUNDS[2], BOUNDS[3], rows_out)
+    lon_ax = ob.lattice_axis(BOUNDS[0], BOUNDS[1], rows_out)
+    r0 = rows_out // 2 - sample_rows // 2
+    pts = np.zeros((sample_rows * rows_out, 3))
+    pts[:, 0] = np.tile(lon_ax, sample_rows)
+    pts[:, 1] = np.repeat(lat_ax[r0:r0 + sample_rows], rows_out)
+    if ob.ref_available():
+        eng, kind = ob.Reference(z, *BOUNDS), "reference"
+        run = lambda: eng.batch(method, pts, threads=threads)
+        cores = threads
+    else:
+        eng, kind = ob.Oracle(z, *BOUNDS), "port"
+        run = lambda: eng.batch(method, pts)
+        cores = 1
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = run()
+    dt = (time.perf_counter() - t0) / steps
+    assert np.isfinite(out).all()
+    sample = (f"{sample_rows} consecutive output rows x {rows_out} columns ({pts.shape[0]} cells) of the same "
+              f"65533^2 lattice, GridH::batchCubicInterpolate")
+    return pts.shape[0] / dt / 1e6, kind, cores, dt * 1e3, sample
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rate, kind, cores, ms, sample = cpu_reference_rate(CPU_SAMPLE_ROWS, threads, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "Mcells/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[3]: synthetic 16384x16384 depth grid, 4x bicubic upsample",
+                       "grid": [N_GRID, N_GRID], "factor": FACTOR, "method": "bicubic Catmull-Rom",
+                       "step": "bounded sample: " + sample},
+            "cpu_baseline": {"value": rate, "unit": "Mcells/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": rate, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the informational per-method table")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import auvi
+    auvi.load()
+    if not torch.cuda.is_available() or auvi.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: libauvi has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, (world, args.gpus)
+
+    # ---- the rank's share of the global problem ---------------------------------------------------
+    n_lon = N_GRID
+    n_lat_global = N_GRID * world
+    out_rows_global = FACTOR * (n_lat_global - 1) + 1
+    out_cols = FACTOR * (n_lon - 1) + 1
+    per = (out_rows_global + world - 1) // world
+    row_lo, row_hi = rank * per, min(out_rows_global, (rank + 1) * per)
+    halo = 12
+    in_lo = max(0, row_lo // FACTOR - halo)
+    in_hi = min(n_lat_global, (row_hi - 1) // FACTOR + 2 + halo)
+    bounds = (BOUNDS[0], BOUNDS[1], BOUNDS[2], BOUNDS[2] + (BOUNDS[3] - BOUNDS[2]) * world)
+    z = synth_grid_device(torch, n_lat_global, n_lon, in_lo, in_hi, dev)
+    g = auvi.Grid(adopt=dict(ptr=z.data_ptr(), dtype=auvi.F32, n_lat=n_lat_global, n_lon=n_lon, ld=n_lon, row0=in_lo,
+                             rows=in_hi - in_lo, keep=z), min_lon=bounds[0], max_lon=bounds[1], min_lat=bounds[2],
+                  max_lat=bounds[3], device=local)
+    out_ld = (out_cols + 3) // 4 * 4                                # 16-byte row pitch
+    my_rows = row_hi - row_lo
+    out = torch.empty((my_rows, out_ld), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    cells_rank = my_rows * out_cols
+    cells_total = out_rows_global * out_cols
+
+    def step(method=auvi.CUBIC):
+        g.lattice_device(method, auvi.AXIS_EXPANDED, FACTOR, FACTOR, 0, row_lo, row_hi, out.data_ptr(), out_ld, None, stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = auvi.launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = auvi.launch_count() - l0
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms / steps, launches
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_step, launches = timed(step, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    value = cells_total / (ms_step * 1e-3) / 1e6
+    peak, peak_src = _peaks()
+    achieved = ALGO_BYTES_PER_CELL * cells_rank / (ms_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": _traffic(), "kernel": "upsample_tiled_kernel<float,CUBIC>", "peak_source": peak_src,
+                "algorithmic_bytes_per_cell": ALGO_BYTES_PER_CELL, "tma": bool(g.uses_tma)}
+
+    # ---- end to end: host buffers through the C-ABI (grid upload + every output cell back) ----------
+    e2e = None
+    if not args.no_e2e:
+        e2e_rows = my_rows
+        try:
+            h_out = torch.empty((e2e_rows, out_cols), dtype=torch.float32, pin_memory=True)
+            h_z = torch.empty((in_hi - in_lo, n_lon), dtype=torch.float32, pin_memory=True)
+        except Exception:
+            h_out = torch.empty((e2e_rows, out_cols), dtype=torch.float32)
+            h_z = torch.empty((in_hi - in_lo, n_lon), dtype=torch.float32)
+        h_z.copy_(z)
+        lib = auvi.load()
+        import ctypes as C
+
+        def e2e_step():
+            # what a caller with host arrays does: upload the slab, run, get every cell back, release
+            h = C.c_void_p()
+            # the slab is passed as a complete grid of its own rows only when world == 1; otherwise adopt needs
+            # device memory, so upload with cudaMemcpy through torch (plumbing) and adopt
+            if world == 1:
+                rc = lib.auvi_grid_create(h_z.data_ptr(), auvi.F32, n_lat_global, n_lon, *bounds, local, C.byref(h))
+                assert rc == 0, lib.auvi_last_error()
+                keep = None
+            else:
+                keep = h_z.to(dev, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                rc = lib.auvi_grid_adopt(keep.data_ptr(), auvi.F32, n_lat_global, n_lon, n_lon, in_lo, in_hi - in_lo,
+                                         *bounds, local, C.byref(h))
+                assert rc == 0, lib.auvi_last_error()
+            rc = lib.auvi_lattice(h, auvi.CUBIC, auvi.AXIS_EXPANDED, FACTOR, FACTOR, 0, row_lo, row_hi, h_out.data_ptr())
+            assert rc == 0, lib.auvi_last_error()
+            lib.auvi_grid_destroy(h)
+
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(1):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        if dist is not None:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": cells_total / dt / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": int(h_z.numel() * 4),
+               "d2h_bytes_per_step": int(e2e_rows * out_cols * 4), "ms_per_step": dt * 1e3, "steps": e2e_steps,
+               "pinned_host": bool(h_out.is_pinned()),
+               "api": "auvi_grid_create + auvi_lattice(host_out) + auvi_grid_destroy"}
+        # spot check: the host result equals the device-resident result
+        chk = slice(my_rows // 2, my_rows // 2 + 8)
+        assert torch.equal(h_out[chk], out[chk, :out_cols].cpu())
+        del h_out, h_z
+
+    # ---- informational: other methods / configs ----------------------------------------------------
+    extra = {}
+    if not args.no_extra:
+        ms_b, _ = timed(lambda: step(auvi.BILINEAR), max(3, args.steps // 2), 2)
+        extra["bilinear_4x_upsample_f32"] = {"Mcells_per_s": cells_total / (ms_b * 1e-3) / 1e6, "ms": ms_b,
+                                             "hbm_frac": ALGO_BYTES_PER_CELL * cells_rank / (ms_b * 1e-3) / 1e9 / peak}
+        if rank == 0:
+            extra.update(extra_gap_fill(torch, auvi, dev, stream, peak))
+            extra.update(extra_mariana(torch, auvi, local))
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        rate, kind, cores, ms_cpu, sample = cpu_reference_rate(CPU_SAMPLE_ROWS, threads)
+        cpu = {"value": rate, "unit": "Mcells/s", "cores": cores, "kind": kind, "sample": sample}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "BASELINE configs[3]: synthetic 16384x16384 FP32 depth grid, 4x bicubic upsample "
+                                       "(per GPU; N GPUs hold a (16384*N) x 16384 grid, output rows sharded)",
+                           "grid_per_gpu": [N_GRID, N_GRID], "factor": FACTOR, "method": "bicubic Catmull-Rom",
+                           "out_cells_per_gpu": cells_rank, "parallelism": f"row-sharded x{world}, halo {halo} rows, no collective",
+                           "l2_policy": "inputs (1.07 GB) and outputs (17.2 GB) per step exceed the 126 MB L2"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+                "extra": extra}
+        print(json.dumps(line), flush=True)
+    g.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def extra_gap_fill(torch, auvi, dev, stream, peak):
+    """BASELINE configs[4] scaled to one GPU: 16384^2 FP32 at 70 % mask, full-grid gap fill."""
+    n = 16384
+    res = {}
+    z = synth_grid_device(torch, n, n, 0, n, dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(42)
+    mask = torch.rand((n, n), device=dev, generator=gen) < 0.70
+    z[mask] = float("nan")
+    del mask
+    g = auvi.Grid(adopt=dict(ptr=z.data_ptr(), dtype=auvi.F32, n_lat=n, n_lon=n, ld=n, row0=0, rows=n, keep=z),
+                  min_lon=100.0, max_lon=110.0, min_lat=-10.0, max_lat=0.0, device=dev.index)
+    out = torch.empty((n, n), dtype=torch.float32, device=dev)
+    for name, meth in (("idw", auvi.IDW), ("nn", auvi.NN), ("kriging", auvi.KRIGING), ("nearest4_mean(cubic fallback)", auvi.CUBIC)):
+        fn = lambda: g.lattice_device(meth, auvi.AXIS_NODES, 1, 1, 1, 0, n, out.data_ptr(), n, None, stream)
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        res[f"gap_fill_70pct_{name}_16384sq_f32"] = {"Mcells_per_s": n * n / (ms * 1e-3) / 1e6, "ms": ms,
+                                                      "hbm_frac": 8.0 * n * n / (ms * 1e-3) / 1e9 / peak}
+    g.close()
+    return res
+
+
+def extra_mariana(torch, auvi, local):
+    """BASELINE configs[1]: Mariana tile at 50 % removal through the Point-list API (host buffers), all
+    methods, with RMSE against the unmasked truth computed on the device."""
+    from oracle import binding as ob          # fixture loader only (tile + seed-42 mask), not the computation
+    case = ob.masked_case("mariana", 0.5)
+    g = auvi.Grid(case["z"], *case["bounds"], device=local)
+    d_truth = torch.from_numpy(case["truth"]).cuda()
+    res = {}
+    for name, meth in (("bilinear", auvi.BILINEAR), ("cubic", auvi.CUBIC), ("kriging", auvi.KRIGING),
+                       ("nn", auvi.NN), ("idw", auvi.IDW)):
+        g.interp_points(meth, case["pts"])
+        t0 = time.perf_counter()
+        for _ in range(5):
+            est = g.interp_points(meth, case["pts"])
+        dt = (time.perf_counter() - t0) / 5
+        d_est = torch.from_numpy(est).cuda()
+        mae, rmse, mx, n_nan = auvi.error_metrics_device(d_truth.data_ptr(), d_est.data_ptr(), auvi.F64, est.size)
+        res[f"mariana50_points_{name}"] = {"Mpts_per_s_e2e": est.size / dt / 1e6, "ms_e2e": dt * 1e3,
+                                           "kernel_ms": g.last_kernel_ms, "rmse_m": rmse, "mae_m": mae, "max_m": mx,
+                                           "n_nan": n_nan, "n": int(est.size)}
+    g.close()
+    return res
+
+
+if __name__ == "__main__":
+    main()
