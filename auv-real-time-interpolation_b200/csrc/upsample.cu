@@ -35,7 +35,9 @@
 
 namespace auvi {
 
-constexpr int kTileCols = 256;     // output columns per CTA = threads per CTA
+constexpr int kColThreads = 128;   // threads along the output columns; each owns 16 bytes of every row
+constexpr int kRowGroups = 2;      // row halves of a tile, swept by separate thread groups
+constexpr int kTileThreads = kColThreads * kRowGroups;
 constexpr int kTileRowsMax = 128;  // output rows per CTA (upper bound; host picks TJ <= this)
 
 struct AxisDev {
@@ -55,6 +57,7 @@ struct TileParams {
     int tj;                        // output rows per CTA
     int bw, bh;                    // shared-memory input box (elements)
     int use_tma;
+    int vec_ok;                    // out and out_ld are 16-byte aligned: vector stores allowed
 };
 
 __device__ __forceinline__ void cr_weights(float t, float& w0, float& w1, float& w2, float& w3) {
@@ -69,21 +72,42 @@ __device__ __forceinline__ void cr_weights(float t, float& w0, float& w1, float&
 template <typename T> __device__ __forceinline__ void store_stream(T* p, T v);
 template <> __device__ __forceinline__ void store_stream<float>(float* p, float v) { __stcs(p, v); }
 template <> __device__ __forceinline__ void store_stream<double>(double* p, double v) { __stcs(p, v); }
+// one 16-byte streaming store per thread and output row
+__device__ __forceinline__ void store_stream_vec(float* p, const float (&v)[4]) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+}
+__device__ __forceinline__ void store_stream_vec(double* p, const double (&v)[2]) {
+    __stcs(reinterpret_cast<double2*>(p), make_double2(v[0], v[1]));
+}
 
+// Out-of-line exact evaluation of one lattice cell (NaN in the footprint, or out of bounds): keeps
+// the ring search and its local arrays out of the streaming loop's register budget.
 template <typename T, int METHOD>
-__global__ void __launch_bounds__(kTileCols, 4)
-upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const TileParams<T> p) {
+__device__ __noinline__ T lattice_cell_exact(const TileParams<T>* p, int64_t J, int I) {
+    return static_cast<T>(interp_exact<T>(p->g, METHOD, __ldg(p->lon.coord + I), __ldg(p->lat.coord + J),
+                                          __ldg(p->lon.pos + I), __ldg(p->lat.pos + J), nullptr));
+}
+
+// CTA = 128 column threads x 2 row groups.  A column thread owns COLS = 16/sizeof(T) adjacent output
+// columns (one 16-byte vector store per output row); a row group sweeps its half of the tile's rows
+// top to bottom, keeping the horizontal pass of the TAPS input rows under the current output row in
+// registers and sliding that window as the (group-uniform) latitude table advances.
+template <typename T, int METHOD>
+__global__ void __launch_bounds__(kTileThreads, sizeof(T) == 4 ? 4 : 3)
+upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileParams<T> p) {
     constexpr bool kCubic = (METHOD == CUBIC);
     constexpr int LO = kCubic ? 1 : 0;            // taps start at base-LO
     constexpr int TAPS = kCubic ? 4 : 2;
     constexpr bool kF64 = sizeof(T) == 8;
+    constexpr int COLS = 16 / static_cast<int>(sizeof(T));
+    constexpr int kTileCols = kColThreads * COLS;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* tile = reinterpret_cast<T*>(smem_raw);                      // [bh][bw]
     __shared__ uint64_t bar;
     __shared__ int s_top[kTileRowsMax];                            // local row of the first tap
-    __shared__ double s_ty[kTileRowsMax];                          // frac(pos_y), NaN if out of bounds
-    __shared__ float4 s_wy[kTileRowsMax];                          // FP32 vertical tap weights
+    __shared__ double s_ty[kF64 ? kTileRowsMax : 1];               // frac(pos_y), NaN if out of bounds
+    __shared__ float4 s_wy[kF64 ? 1 : kTileRowsMax];               // FP32 vertical tap weights
 
     const int tid = threadIdx.x;
     const int W = p.lon.n;
@@ -93,8 +117,7 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const TileParams
     // global column of tile column 0, rounded down to a 16-byte boundary: with no swizzle/interleave
     // the TMA unit faults ("illegal instruction") on a box whose first element is not 16-byte aligned
     // in global memory (measured on B200: profiles/r01_tma_alignment_probe.txt)
-    constexpr int kAlign = 16 / static_cast<int>(sizeof(T));
-    const int c0 = (__ldg(p.lon.base + I0) - LO) & ~(kAlign - 1);
+    const int c0 = (__ldg(p.lon.base + I0) - LO) & ~(COLS - 1);
     const int r0 = __ldg(p.lat.base + J0) - LO;                    // global row of tile row 0
     const int bw = p.bw, bh = p.bh;
 
@@ -107,7 +130,7 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const TileParams
             tma_load_2d(tile, &tmap, c0, r0 - p.g.row0, &bar);
         }
     } else {
-        for (int k = tid; k < bw * bh; k += kTileCols) {           // coalesced, clamp-to-edge
+        for (int k = tid; k < bw * bh; k += kTileThreads) {        // coalesced, clamp-to-edge
             int lr = k / bw, lc = k - lr * bw;
             int gr = clampi(r0 + lr, 0, p.g.n_lat - 1), gc = clampi(c0 + lc, 0, p.g.n_lon - 1);
             tile[k] = __ldg(p.g.z + static_cast<int64_t>(gr - p.g.row0) * p.g.ld + gc);
@@ -120,23 +143,32 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const TileParams
         const int by = __ldg(p.lat.base + J0 + tid);
         const double ty = dsub(py, static_cast<double>(by));       // NaN stays NaN
         s_top[tid] = by - LO - r0;
-        s_ty[tid] = ty;
-        float4 w;
-        if (kCubic) cr_weights(static_cast<float>(ty), w.x, w.y, w.z, w.w);
-        else { w.x = 1.f - static_cast<float>(ty); w.y = static_cast<float>(ty); w.z = 0.f; w.w = 0.f; }
-        s_wy[tid] = w;
+        if constexpr (kF64) {
+            s_ty[tid] = ty;
+        } else {
+            float4 w;
+            if (kCubic) cr_weights(static_cast<float>(ty), w.x, w.y, w.z, w.w);
+            else { w.x = 1.f - static_cast<float>(ty); w.y = static_cast<float>(ty); w.z = 0.f; w.w = 0.f; }
+            s_wy[tid] = w;
+        }
     }
-    const int I = I0 + tid;
-    const bool active = I < W;
-    double px = qnan();
-    int bx = c0 + LO;
-    if (active) { px = __ldg(p.lon.pos + I); bx = __ldg(p.lon.base + I); }
-    const double txd = active ? dsub(px, static_cast<double>(bx)) : 0.0;
-    const int ox = bx - LO - c0;
-    float wx0 = 0.f, wx1 = 0.f, wx2 = 0.f, wx3 = 0.f;
-    if (!kF64) {
-        if (kCubic) cr_weights(static_cast<float>(txd), wx0, wx1, wx2, wx3);
-        else { wx0 = 1.f - static_cast<float>(txd); wx1 = static_cast<float>(txd); }
+    const int ct = tid % kColThreads, rg = tid / kColThreads;
+    const int Ic = I0 + ct * COLS;                                 // first of this thread's columns
+    int ox[COLS];
+    double txd[COLS];
+    float wx[kF64 ? 1 : COLS][4];
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+        const int I = Ic + c;
+        double px = 0.0;
+        int bx = c0 + LO;
+        if (I < W) { px = __ldg(p.lon.pos + I); bx = __ldg(p.lon.base + I); }
+        txd[c] = dsub(px, static_cast<double>(bx));
+        ox[c] = bx - LO - c0;
+        if constexpr (!kF64) {
+            if (kCubic) cr_weights(static_cast<float>(txd[c]), wx[c][0], wx[c][1], wx[c][2], wx[c][3]);
+            else { wx[c][0] = 1.f - static_cast<float>(txd[c]); wx[c][1] = static_cast<float>(txd[c]); wx[c][2] = 0.f; wx[c][3] = 0.f; }
+        }
     }
 
     if (p.use_tma) {
@@ -145,7 +177,7 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const TileParams
         // zero-fills instead, so border tiles copy the edge row/column into their out-of-grid halo.
         const bool border = c0 < 0 || c0 + bw > p.g.n_lon || r0 < 0 || r0 + bh > p.g.n_lat;
         if (border) {
-            for (int k = tid; k < bw * bh; k += kTileCols) {
+            for (int k = tid; k < bw * bh; k += kTileThreads) {
                 int lr = k / bw, lc = k - lr * bw;
                 int gr = r0 + lr, gc = c0 + lc;
                 int cr = clampi(gr, 0, p.g.n_lat - 1), cc = clampi(gc, 0, p.g.n_lon - 1);
@@ -157,55 +189,102 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const TileParams
         }
     }
     __syncthreads();
+    if (Ic >= W) return;
 
-    // ---- horizontal pass of one tile row for this thread's column --------------------------------
-    auto hrow = [&](int lr) -> T {
-        lr = min(lr, bh - 1);                                      // window rows past the box are unused
-        const T* r = tile + lr * bw + ox;
-        if constexpr (kF64) {
-            if constexpr (kCubic) return catmull_rom_exact(r[0], r[1], r[2], r[3], txd);
-            else return dadd(dmul(dsub(1.0, txd), r[0]), dmul(txd, r[1]));
-        } else {
-            if constexpr (kCubic) return fmaf(wx3, r[3], fmaf(wx2, r[2], fmaf(wx1, r[1], wx0 * r[0])));
-            else return fmaf(wx1, r[1], wx0 * r[0]);
+    // this row group's share of the tile rows
+    const int per_group = (nJ + kRowGroups - 1) / kRowGroups;
+    const int jr_begin = rg * per_group, jr_end = min(nJ, jr_begin + per_group);
+    if (jr_begin >= jr_end) return;
+    const bool full = p.vec_ok && (Ic + COLS <= W);
+    T* out_row = p.out + (J0 - p.row_begin + jr_begin) * p.out_ld + Ic;
+    const int64_t out_ld = p.out_ld;
+
+    // ---- horizontal pass of one tile row for this thread's columns --------------------------------
+    // A NaN anywhere in a footprint (or a NaN weight: out of bounds) surfaces in the horizontal pass
+    // of some row the output uses, so it is enough to probe those (cheaper than probing every output).
+    T probe = 0;
+    auto hrow = [&](const T* r, T (&dst)[COLS]) {
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) {
+            const T* q = r + ox[c];
+            if constexpr (kF64) {
+                if constexpr (kCubic) dst[c] = catmull_rom_exact(q[0], q[1], q[2], q[3], txd[c]);
+                else dst[c] = dadd(dmul(dsub(1.0, txd[c]), q[0]), dmul(txd[c], q[1]));
+            } else {
+                if constexpr (kCubic) dst[c] = fmaf(wx[c][3], q[3], fmaf(wx[c][2], q[2], fmaf(wx[c][1], q[1], wx[c][0] * q[0])));
+                else dst[c] = fmaf(wx[c][1], q[1], wx[c][0] * q[0]);
+            }
+            probe += dst[c];
         }
     };
-
-    T h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-    int top = -(1 << 20);
-    T* out_col = p.out + (J0 - p.row_begin) * p.out_ld + I;
-    for (int jr = 0; jr < nJ; ++jr) {
-        const int t = s_top[jr];                                   // warp-uniform
-        if (t != top) {
-            const int shift = t - top;
-            if (shift == 1) { h0 = h1; h1 = h2; h2 = h3; h3 = hrow(t + TAPS - 1); if (!kCubic) h1 = hrow(t + 1); }
-            else if (shift == 2 && kCubic) { h0 = h2; h1 = h3; h2 = hrow(t + 2); h3 = hrow(t + 3); }
-            else {
-                h0 = hrow(t); h1 = hrow(t + 1);
-                if (kCubic) { h2 = hrow(t + 2); h3 = hrow(t + 3); }
-            }
-            top = t;
-        }
-        T v;
+    // one output row from the window; `ph` = slot holding the window's first row (a constant once the
+    // phase loop below is unrolled, so the window never moves between registers)
+    auto emit = [&](int jr, const T (&h)[TAPS][COLS], int ph) {
+        T v[COLS];
         if constexpr (kF64) {
             const double ty = s_ty[jr];
-            if constexpr (kCubic) v = catmull_rom_exact(h0, h1, h2, h3, ty);
-            else v = dadd(dmul(dsub(1.0, ty), h0), dmul(ty, h1));
+            probe += ty;
+#pragma unroll
+            for (int c = 0; c < COLS; ++c) {
+                if constexpr (kCubic)
+                    v[c] = catmull_rom_exact(h[ph % TAPS][c], h[(ph + 1) % TAPS][c], h[(ph + 2) % TAPS][c], h[(ph + 3) % TAPS][c], ty);
+                else v[c] = dadd(dmul(dsub(1.0, ty), h[ph % TAPS][c]), dmul(ty, h[(ph + 1) % TAPS][c]));
+            }
         } else {
             const float4 w = s_wy[jr];
-            if constexpr (kCubic) v = fmaf(w.w, h3, fmaf(w.z, h2, fmaf(w.y, h1, w.x * h0)));
-            else v = fmaf(w.y, h1, w.x * h0);
-        }
-        if (active) {
-            if (isnan(v)) {                                        // NaN in the footprint, or out of bounds
-                const int64_t J = J0 + jr;
-                const double py = __ldg(p.lat.pos + J);
-                v = static_cast<T>(interp_exact<T>(p.g, METHOD, __ldg(p.lon.coord + I), __ldg(p.lat.coord + J),
-                                                   px, py, nullptr));
+            probe += w.x;
+#pragma unroll
+            for (int c = 0; c < COLS; ++c) {
+                if constexpr (kCubic)
+                    v[c] = fmaf(w.w, h[(ph + 3) % TAPS][c], fmaf(w.z, h[(ph + 2) % TAPS][c], fmaf(w.y, h[(ph + 1) % TAPS][c], w.x * h[ph % TAPS][c])));
+                else v[c] = fmaf(w.y, h[(ph + 1) % TAPS][c], w.x * h[ph % TAPS][c]);
             }
-            store_stream<T>(out_col, v);
         }
-        out_col += p.out_ld;
+        if (full) {
+            store_stream_vec(out_row, v);
+        } else {
+#pragma unroll
+            for (int c = 0; c < COLS; ++c)
+                if (Ic + c < W) store_stream<T>(out_row + c, v[c]);
+        }
+        out_row += out_ld;
+    };
+
+    T h[TAPS][COLS];
+    int jr = jr_begin;
+    int top = s_top[jr];                                           // window = tile rows [top, top+TAPS)
+    const T* next_row = tile + top * bw;
+#pragma unroll
+    for (int k = 0; k < TAPS; ++k, next_row += bw) hrow(next_row, h[k]);
+#pragma unroll 1
+    for (;;) {
+#pragma unroll
+        for (int ph = 0; ph < TAPS; ++ph) {                        // slot (ph+k)%TAPS holds tile row top+k
+#pragma unroll 1
+            while (jr < jr_end && s_top[jr] == top) {              // uniform across the row group
+                emit(jr, h, ph);
+                ++jr;
+            }
+            if (jr >= jr_end) goto swept;
+            hrow(next_row, h[ph]);                                 // the oldest slot takes tile row top+TAPS
+            next_row += bw;
+            ++top;
+        }
+    }
+swept:
+    const bool dirty = isnan(probe);
+    if (!dirty) return;
+    // ---- second sweep, only for threads that produced a NaN: re-read the cells this thread wrote
+    // and replace every NaN by the exact per-query evaluation (ring-search fallbacks, NaN-corner
+    // means, out-of-bounds NaN).  Kept out of the streaming loop so that the call and its local
+    // arrays do not cost the clean path registers.
+    out_row = p.out + (J0 - p.row_begin + jr_begin) * p.out_ld + Ic;
+    for (int jr = jr_begin; jr < jr_end; ++jr, out_row += p.out_ld) {
+#pragma unroll 1
+        for (int c = 0; c < COLS; ++c) {
+            if (Ic + c >= W) break;
+            if (isnan(out_row[c])) store_stream<T>(out_row + c, lattice_cell_exact<T, METHOD>(&p, J0 + jr, Ic + c));
+        }
     }
 }
 
@@ -302,8 +381,9 @@ static cudaError_t launch_tiled(const GridDesc& d, const AxisTables& lat, const 
     const int lo = METHOD == CUBIC ? 1 : 0;
     const size_t es = sizeof(T);
     const int align = static_cast<int>(16 / es);
-    int tj = 64;
-    int bw = max_span(lon.h_base, 0, lon.n, kTileCols, taps, lo, align);
+    int tj = kTileRowsMax;
+    const int tile_cols = kColThreads * align;
+    int bw = max_span(lon.h_base, 0, lon.n, tile_cols, taps, lo, align);
     bw = (bw + align - 1) / align * align;
     int bh = max_span(lat.h_base, row_begin, row_end, tj, taps, lo, 1);
     while (static_cast<size_t>(bw) * bh * es > 96 * 1024 && tj > 8) {       // keep >=2 CTAs/SM of smem
@@ -325,6 +405,7 @@ static cudaError_t launch_tiled(const GridDesc& d, const AxisTables& lat, const 
     p.row_begin = row_begin; p.row_end = row_end;
     p.out = static_cast<T*>(out); p.out_ld = out_ld;
     p.tj = tj; p.bw = bw; p.bh = bh;
+    p.vec_ok = (reinterpret_cast<uintptr_t>(out) % 16 == 0 && (out_ld * es) % 16 == 0) ? 1 : 0;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
     // The tensor map covers the resident slab; box rows outside it are zero-filled.  The slab check
@@ -338,9 +419,9 @@ static cudaError_t launch_tiled(const GridDesc& d, const AxisTables& lat, const 
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
     }
-    dim3 grid(static_cast<unsigned>((lon.n + kTileCols - 1) / kTileCols),
+    dim3 grid(static_cast<unsigned>((lon.n + tile_cols - 1) / tile_cols),
               static_cast<unsigned>((row_end - row_begin + tj - 1) / tj));
-    kern<<<grid, kTileCols, smem, st>>>(tmap, p);
+    kern<<<grid, kTileThreads, smem, st>>>(tmap, p);
     if (info) { info->launches += 1; info->used_tma = p.use_tma; }
     return cudaGetLastError();
 }
