@@ -199,11 +199,9 @@ def main():
     n_lat_global = N_GRID * world
     out_rows_global = FACTOR * (n_lat_global - 1) + 1
     out_cols = FACTOR * (n_lon - 1) + 1
-    per = (out_rows_global + world - 1) // world
-    row_lo, row_hi = rank * per, min(out_rows_global, (rank + 1) * per)
-    halo = 12
-    in_lo = max(0, row_lo // FACTOR - halo)
-    in_hi = min(n_lat_global, (row_hi - 1) // FACTOR + 2 + halo)
+    import shard
+    plan = shard.plan_rows(n_lat_global, FACTOR, world, rank)
+    row_lo, row_hi, in_lo, in_hi, halo = plan.row_lo, plan.row_hi, plan.in_lo, plan.in_hi, shard.HALO
     bounds = (BOUNDS[0], BOUNDS[1], BOUNDS[2], BOUNDS[2] + (BOUNDS[3] - BOUNDS[2]) * world)
     z = synth_grid_device(torch, n_lat_global, n_lon, in_lo, in_hi, dev)
     g = auvi.Grid(adopt=dict(ptr=z.data_ptr(), dtype=auvi.F32, n_lat=n_lat_global, n_lon=n_lon, ld=n_lon, row0=in_lo,
@@ -260,7 +258,10 @@ def main():
     # ---- end to end: host buffers through the C-ABI (grid upload + every output cell back) ----------
     e2e = None
     if not args.no_e2e:
-        e2e_rows = my_rows
+        with open("/proc/meminfo") as f:
+            avail = next(int(l.split()[1]) for l in f if l.startswith("MemAvailable")) * 1024
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        e2e_rows = shard.e2e_row_budget(my_rows, out_cols * 4, avail, local_world)
         try:
             h_out = torch.empty((e2e_rows, out_cols), dtype=torch.float32, pin_memory=True)
             h_z = torch.empty((in_hi - in_lo, n_lon), dtype=torch.float32, pin_memory=True)
@@ -286,7 +287,7 @@ def main():
                 rc = lib.auvi_grid_adopt(keep.data_ptr(), auvi.F32, n_lat_global, n_lon, n_lon, in_lo, in_hi - in_lo,
                                          *bounds, local, C.byref(h))
                 assert rc == 0, lib.auvi_last_error()
-            rc = lib.auvi_lattice(h, auvi.CUBIC, auvi.AXIS_EXPANDED, FACTOR, FACTOR, 0, row_lo, row_hi, h_out.data_ptr())
+            rc = lib.auvi_lattice(h, auvi.CUBIC, auvi.AXIS_EXPANDED, FACTOR, FACTOR, 0, row_lo, row_lo + e2e_rows, h_out.data_ptr())
             assert rc == 0, lib.auvi_last_error()
             lib.auvi_grid_destroy(h)
 
@@ -303,12 +304,13 @@ def main():
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": cells_total / dt / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": int(h_z.numel() * 4),
+        e2e_cells = cells_total * (e2e_rows / my_rows)      # == cells_total unless host memory forced a row cut
+        e2e = {"value": e2e_cells / dt / 1e6, "unit": "Mcells/s", "rows_per_rank": e2e_rows, "rows_of_shard": my_rows, "h2d_bytes_per_step": int(h_z.numel() * 4),
                "d2h_bytes_per_step": int(e2e_rows * out_cols * 4), "ms_per_step": dt * 1e3, "steps": e2e_steps,
                "pinned_host": bool(h_out.is_pinned()),
                "api": "auvi_grid_create + auvi_lattice(host_out) + auvi_grid_destroy"}
         # spot check: the host result equals the device-resident result
-        chk = slice(my_rows // 2, my_rows // 2 + 8)
+        chk = slice(e2e_rows // 2, e2e_rows // 2 + 8)
         assert torch.equal(h_out[chk], out[chk, :out_cols].cpu())
         del h_out, h_z
 
