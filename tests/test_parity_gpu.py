@@ -448,3 +448,72 @@ def test_config5_gap_fill_properties_at_scale(auvi, torch):
             assert bool(same.all()), "gap fill is not idempotent"
             g_f.close()
     g.close()
+
+
+# ---- BASELINE configs 0/2 at their full sizes ---------------------------------------------------------------
+@pytest.mark.parametrize("name", ["mariana", "east_pacific", "mid_atlantic"])
+@pytest.mark.parametrize("frac", [0.10, 0.50, 0.90])
+def test_config2_all_regions_every_method(auvi, torch, name, frac):
+    """BASELINE config 2: every bundled region (Kerguelen's tile is missing from the checkout) at 10/50/90 %
+    removal, every method, as a full-grid gap fill: per-point parity with the oracle on EVERY removed cell
+    and the MAE/RMSE/Max/NaN-count rows computed with the unmodified reference (golden_metrics.json)."""
+    case = ob.masked_case(name, frac)
+    m = case["meta"]
+    orc = ob.Oracle(case["z"], *case["bounds"])
+    g = auvi.Grid(case["z"], *case["bounds"])
+    rows, cols = case["rows"], case["cols"]
+    d_truth = torch.from_numpy(case["truth"]).cuda()
+    key = f"{name}@{frac:.2f}"
+    for meth in METHODS:
+        filled = g.lattice(meth, auvi.AXIS_NODES, 1, 1, fill=1)
+        got = filled[rows, cols]
+        want = orc.batch(meth, case["pts"])
+        if meth in (ob.BILINEAR, ob.CUBIC, ob.NN):
+            assert bits_equal(got, want), (key, ob.METHOD_NAMES[meth])
+        elif meth == ob.KRIGING:
+            _close(got, want, atol=TIGHT, rtol=0)
+        else:
+            _close(got, want)
+        if meth in (ob.BILINEAR, ob.CUBIC, ob.KRIGING):
+            d_est = torch.from_numpy(np.ascontiguousarray(got)).cuda()
+            mae, rmse, mx, n_nan = auvi.error_metrics_device(d_truth.data_ptr(), d_est.data_ptr(), auvi.F64, got.size)
+            gold = _G["computed"][key][ob.METHOD_NAMES[meth]]
+            assert n_nan == gold["n_nan"] and got.size == gold["n"]
+            np.testing.assert_allclose([mae, rmse, mx], [gold["mae"], gold["rmse"], gold["max"]], rtol=1e-9)
+    g.close()
+
+
+def test_config0_grid_a_full_size(auvi):
+    """BASELINE config 0 at the reference generator's shipped size: the 4000 x 3200 synthetic Grid A
+    (generate_csv_grids.cpp:99-104, values through the 6-digit CSV), 2x expanded lattice 7999 x 6399 =
+    51.2 M queries (test_interpolation.cpp:283-297).  Bilinear and bicubic: bit-identical to the oracle on
+    every cell; kriging / NN / IDW on a band of rows."""
+    n_lat, n_lon = 3200, 4000
+    z = ob.synth_grid(n_lat, n_lon)
+    bounds = (-180.0, -160.0, 20.0, 30.0)
+    g = auvi.Grid(z, *bounds)
+    orc = ob.Oracle(z, *bounds)
+    nn_lat, nn_lon = g.lattice_dims(auvi.AXIS_EXPANDED, 2, 2)
+    assert (nn_lat, nn_lon) == (6399, 7999)
+    lat_ax = ob.lattice_axis(bounds[2], bounds[3], nn_lat)
+    lon_ax = ob.lattice_axis(bounds[0], bounds[1], nn_lon)
+    for meth in (ob.BILINEAR, ob.CUBIC):
+        got = g.lattice(meth, auvi.AXIS_EXPANDED, 2, 2)
+        for r0 in range(0, nn_lat, 800):                       # oracle in row blocks to bound host memory
+            r1 = min(nn_lat, r0 + 800)
+            pts = np.zeros(((r1 - r0) * nn_lon, 3))
+            pts[:, 0] = np.tile(lon_ax, r1 - r0)
+            pts[:, 1] = np.repeat(lat_ax[r0:r1], nn_lon)
+            assert bits_equal(got[r0:r1].ravel(), orc.batch(meth, pts)), (ob.METHOD_NAMES[meth], r0)
+    r0, r1 = 3000, 3060
+    pts = np.zeros(((r1 - r0) * nn_lon, 3))
+    pts[:, 0] = np.tile(lon_ax, r1 - r0)
+    pts[:, 1] = np.repeat(lat_ax[r0:r1], nn_lon)
+    for meth in (ob.KRIGING, ob.NN, ob.IDW):
+        got = g.lattice(meth, auvi.AXIS_EXPANDED, 2, 2, row_begin=r0, row_end=r1).ravel()
+        want = orc.batch(meth, pts)
+        if meth == ob.NN:
+            assert bits_equal(got, want)
+        else:
+            _close(got, want, atol=TIGHT if meth == ob.KRIGING else ATOL, rtol=0 if meth == ob.KRIGING else RTOL)
+    g.close()
