@@ -16,8 +16,10 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -57,6 +59,60 @@ struct AxisOwned {
     }
 };
 
+// Process-wide cache of large device blocks (grid storage, lattice staging).  cudaMalloc/cudaFree of
+// gigabyte blocks cost up to ~150 ms on a busy context (measured: profiles/r01_e2e_pieces.txt); a caller that
+// creates and destroys grids per batch -- as the reference's drivers do -- should not pay that every time.
+// Blocks are only returned here after the device is idle (auvi_grid_destroy synchronises), so reuse on any
+// stream is safe.  At most kCacheBytes are held; auvi_trim() releases them.
+struct DevBlock { void* p; size_t bytes; int device; };
+std::mutex g_cache_mu;
+std::vector<DevBlock> g_cache;
+size_t g_cache_held = 0;
+constexpr size_t kCacheBytes = 6ull << 30;
+constexpr size_t kCacheMinBlock = 8ull << 20;
+
+cudaError_t cached_malloc(void** out, size_t bytes, int device) {
+    if (bytes >= kCacheMinBlock) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        size_t best = g_cache.size();
+        for (size_t k = 0; k < g_cache.size(); ++k)
+            if (g_cache[k].device == device && g_cache[k].bytes >= bytes && g_cache[k].bytes <= bytes + bytes / 4 &&
+                (best == g_cache.size() || g_cache[k].bytes < g_cache[best].bytes)) best = k;
+        if (best != g_cache.size()) {
+            *out = g_cache[best].p;
+            g_cache_held -= g_cache[best].bytes;
+            g_cache.erase(g_cache.begin() + best);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {                         // give the cache back and retry once
+        cudaGetLastError();
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        for (auto& b : g_cache) cudaFree(b.p);
+        g_cache.clear(); g_cache_held = 0;
+        e = cudaMalloc(out, bytes);
+    }
+    return e;
+}
+
+// `bytes` must be the size the block was allocated with (callers keep it); it may exceed the size asked for.
+void cached_free(void* p, size_t bytes, int device) {
+    if (!p) return;
+    if (bytes >= kCacheMinBlock && bytes <= kCacheBytes) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        while (!g_cache.empty() && g_cache_held + bytes > kCacheBytes) {   // evict oldest
+            cudaFree(g_cache.front().p);
+            g_cache_held -= g_cache.front().bytes;
+            g_cache.erase(g_cache.begin());
+        }
+        g_cache.push_back(DevBlock{p, bytes, device});
+        g_cache_held += bytes;
+        return;
+    }
+    cudaFree(p);
+}
+
 constexpr int64_t kPointChunk = 1 << 20;            // queries per pipeline stage (16 MiB in, 8 MiB out)
 constexpr int64_t kLatticeChunkBytes = 256ll << 20; // device staging per pipeline stage, lattice host form
 
@@ -66,6 +122,7 @@ struct auvi_grid {
     GridDesc d;
     int device = 0;
     void* owned = nullptr;                            // device allocation we must free (create), else null
+    size_t owned_bytes = 0;
     cudaStream_t st[2] = {nullptr, nullptr};
     cudaEvent_t ev_k0[2] = {nullptr, nullptr}, ev_k1[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     // point-list staging (double-buffered)
@@ -180,7 +237,15 @@ int auvi_device_count(void) {
     return n;
 }
 
-int auvi_version(void) { return 100; }
+int auvi_version(void) { return 101; }
+
+int auvi_trim(void) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (auto& b : g_cache) { cudaSetDevice(b.device); cudaFree(b.p); }
+    g_cache.clear();
+    g_cache_held = 0;
+    return 0;
+}
 const char* auvi_last_error(void) { return t_error.c_str(); }
 int64_t auvi_launch_count(void) { return g_launches.load(); }
 float auvi_last_kernel_ms(const auvi_grid* g) { return g ? g->last_ms : 0.f; }
@@ -201,7 +266,8 @@ int auvi_grid_create(const void* host_rowmajor, int dtype, int64_t n_lat, int64_
     // rows padded to a 16-byte pitch so that TMA can address any grid width
     const int64_t ld = (n_lon * es + 15) / 16 * 16 / es;
     cudaError_t e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaMalloc(&g->owned, static_cast<size_t>(ld) * n_lat * es);
+    g->owned_bytes = static_cast<size_t>(ld) * n_lat * es;
+    if (e == cudaSuccess) e = cached_malloc(&g->owned, g->owned_bytes, device);
     if (e == cudaSuccess)
         e = cudaMemcpy2D(g->owned, ld * es, host_rowmajor, n_lon * es, n_lon * es, n_lat, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(g->owned); delete g; return fail_cuda("grid upload", e); }
@@ -244,14 +310,15 @@ int auvi_grid_destroy(auvi_grid* g) {
     for (int k = 0; k < 2; ++k) {
         if (g->h_in[k]) cudaFreeHost(g->h_in[k]);
         if (g->h_out[k]) cudaFreeHost(g->h_out[k]);
-        cudaFree(g->d_in[k]); cudaFree(g->d_out[k]); cudaFree(g->d_rows[k]);
+        cudaFree(g->d_in[k]); cudaFree(g->d_out[k]);
+        cached_free(g->d_rows[k], g->d_rows_bytes, g->device);
         if (g->ev_k0[k]) cudaEventDestroy(g->ev_k0[k]);
         if (g->ev_k1[k]) cudaEventDestroy(g->ev_k1[k]);
         if (g->ev_done[k]) cudaEventDestroy(g->ev_done[k]);
         if (g->st[k]) cudaStreamDestroy(g->st[k]);
     }
     cudaFree(g->d_scratch); cudaFree(g->d_result4);
-    cudaFree(g->owned);
+    cached_free(g->owned, g->owned_bytes, g->device);
     delete g;
     return 0;
 }
@@ -376,14 +443,19 @@ int auvi_lattice(auvi_grid* g, int method, int axis_kind, int f_lat, int f_lon, 
     AUVI_CUDA(cudaSetDevice(g->device));
     const size_t es = g->d.dtype == AUVI_F64 ? 8 : 4;
     const int64_t row_bytes = cols * static_cast<int64_t>(es);
-    int64_t chunk_rows = kLatticeChunkBytes / row_bytes;
+    static const int64_t chunk_bytes = [] {                           // tuning knob, MiB
+        const char* e = getenv("AUVI_LATTICE_CHUNK_MB");
+        const long v = e ? atol(e) : 0;
+        return v > 0 ? static_cast<int64_t>(v) << 20 : kLatticeChunkBytes;
+    }();
+    int64_t chunk_rows = chunk_bytes / row_bytes;
     if (chunk_rows < 1) chunk_rows = 1;
     if (chunk_rows > row_end - row_begin) chunk_rows = row_end - row_begin;
     const size_t need = static_cast<size_t>(chunk_rows) * row_bytes;
     if (need > g->d_rows_bytes) {
-        for (int k = 0; k < 2; ++k) { cudaFree(g->d_rows[k]); g->d_rows[k] = nullptr; }
+        for (int k = 0; k < 2; ++k) { cached_free(g->d_rows[k], g->d_rows_bytes, g->device); g->d_rows[k] = nullptr; }
         g->d_rows_bytes = 0;
-        for (int k = 0; k < 2; ++k) AUVI_CUDA(cudaMalloc(&g->d_rows[k], need));
+        for (int k = 0; k < 2; ++k) AUVI_CUDA(cached_malloc(&g->d_rows[k], need, g->device));
         g->d_rows_bytes = need;
     }
     float ms_total = 0.f;

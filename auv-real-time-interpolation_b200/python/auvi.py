@@ -32,6 +32,7 @@ SYMBOLS = {
     "auvi_grid_create": (_i32, [_vp, _i32, _i64, _i64, _dbl, _dbl, _dbl, _dbl, _i32, C.POINTER(_vp)]),
     "auvi_grid_adopt": (_i32, [_vp, _i32, _i64, _i64, _i64, _i64, _i64, _dbl, _dbl, _dbl, _dbl, _i32, C.POINTER(_vp)]),
     "auvi_grid_destroy": (_i32, [_vp]),
+    "auvi_trim": (_i32, []),
     "auvi_interp_points": (_i32, [_vp, _i32, _vp, _i64, _i64, _vp, _i64]),
     "auvi_interp_points_device": (_i32, [_vp, _i32, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "auvi_lattice_dims": (_i32, [_vp, _i32, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64)]),

@@ -106,11 +106,17 @@ class ClockSampler:
 
 
 def synth_grid_device(torch, n_lat_global, n_lon, row_lo, row_hi, device):
-    """Rows [row_lo,row_hi) of the seamount field (generate_csv_grids.cpp:32-70) in FP32, on device."""
+    """Rows [row_lo,row_hi) of the seamount field (generate_csv_grids.cpp:32-70) in FP32, on device.
+    Evaluated in FP64 in 1024-row blocks so that the temporaries stay small next to the 17 GB outputs."""
+    z = torch.empty((row_hi - row_lo, n_lon), dtype=torch.float32, device=device)
     i = torch.arange(n_lon, device=device, dtype=torch.float64) * (100.0 / (n_lon - 1))
-    j = torch.arange(row_lo, row_hi, device=device, dtype=torch.float64) * (100.0 / (n_lat_global - 1))
-    z = -(10.0 + 2.0 * i)[None, :] + 100.0 * torch.exp(-(((i - 75.0) ** 2)[None, :] + ((j - 50.0) ** 2)[:, None]) / 450.0)
-    return z.to(torch.float32).contiguous()
+    base = -(10.0 + 2.0 * i)[None, :]
+    gx = ((i - 75.0) ** 2)[None, :]
+    for r in range(row_lo, row_hi, 1024):
+        r1 = min(row_hi, r + 1024)
+        j = torch.arange(r, r1, device=device, dtype=torch.float64) * (100.0 / (n_lat_global - 1))
+        z[r - row_lo:r1 - row_lo] = (base + 100.0 * torch.exp(-(gx + ((j - 50.0) ** 2)[:, None]) / 450.0)).to(torch.float32)
+    return z
 
 
 def cpu_reference_rate(sample_rows, threads, steps=1, warmup=0, method=1):
@@ -272,29 +278,38 @@ def main():
         lib = auvi.load()
         import ctypes as C
 
+        pieces = {"upload_ms": 0.0, "lattice_ms": 0.0, "release_ms": 0.0}
+
         def e2e_step():
             # what a caller with host arrays does: upload the slab, run, get every cell back, release
             h = C.c_void_p()
-            # the slab is passed as a complete grid of its own rows only when world == 1; otherwise adopt needs
-            # device memory, so upload with cudaMemcpy through torch (plumbing) and adopt
+            t0 = time.perf_counter()
             if world == 1:
                 rc = lib.auvi_grid_create(h_z.data_ptr(), auvi.F32, n_lat_global, n_lon, *bounds, local, C.byref(h))
                 assert rc == 0, lib.auvi_last_error()
                 keep = None
             else:
+                # a row slab is described by auvi_grid_adopt, which takes device memory: upload it first
                 keep = h_z.to(dev, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
                 rc = lib.auvi_grid_adopt(keep.data_ptr(), auvi.F32, n_lat_global, n_lon, n_lon, in_lo, in_hi - in_lo,
                                          *bounds, local, C.byref(h))
                 assert rc == 0, lib.auvi_last_error()
+            t1 = time.perf_counter()
             rc = lib.auvi_lattice(h, auvi.CUBIC, auvi.AXIS_EXPANDED, FACTOR, FACTOR, 0, row_lo, row_lo + e2e_rows, h_out.data_ptr())
             assert rc == 0, lib.auvi_last_error()
+            t2 = time.perf_counter()
             lib.auvi_grid_destroy(h)
+            del keep
+            t3 = time.perf_counter()
+            pieces["upload_ms"] += (t1 - t0) * 1e3; pieces["lattice_ms"] += (t2 - t1) * 1e3; pieces["release_ms"] += (t3 - t2) * 1e3
 
         e2e_steps = max(1, min(args.steps, 3))
         for _ in range(1):
             e2e_step()
         barrier()
+        for k in pieces:
+            pieces[k] = 0.0
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             e2e_step()
@@ -307,8 +322,20 @@ def main():
         e2e_cells = cells_total * (e2e_rows / my_rows)      # == cells_total unless host memory forced a row cut
         e2e = {"value": e2e_cells / dt / 1e6, "unit": "Mcells/s", "rows_per_rank": e2e_rows, "rows_of_shard": my_rows, "h2d_bytes_per_step": int(h_z.numel() * 4),
                "d2h_bytes_per_step": int(e2e_rows * out_cols * 4), "ms_per_step": dt * 1e3, "steps": e2e_steps,
-               "pinned_host": bool(h_out.is_pinned()),
+               "pinned_host": bool(h_out.is_pinned()), "pieces_ms": {k: v / e2e_steps for k, v in pieces.items()},
                "api": "auvi_grid_create + auvi_lattice(host_out) + auvi_grid_destroy"}
+        # raw pinned device->host copy bandwidth of this box, for context (the e2e step moves 16x more bytes D2H than H2D)
+        try:
+            probe_d = torch.empty(1 << 28, dtype=torch.float32, device=dev)
+            probe_h = torch.empty(1 << 28, dtype=torch.float32, pin_memory=True)
+            probe_h.copy_(probe_d); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            probe_h.copy_(probe_d, non_blocking=True); torch.cuda.synchronize()
+            e2e["pcie_d2h_gbs_raw"] = probe_d.numel() * 4 / (time.perf_counter() - t0) / 1e9
+            e2e["pcie_d2h_gbs_in_e2e"] = e2e["d2h_bytes_per_step"] / dt / 1e9
+            del probe_d, probe_h
+        except Exception:
+            pass
         # spot check: the host result equals the device-resident result
         chk = slice(e2e_rows // 2, e2e_rows // 2 + 8)
         assert torch.equal(h_out[chk], out[chk, :out_cols].cpu())
@@ -323,6 +350,7 @@ def main():
         if rank == 0:
             extra.update(extra_gap_fill(torch, auvi, dev, stream, peak))
             extra.update(extra_mariana(torch, auvi, local))
+            extra.update(extra_grid_a_points(torch, auvi, local))
 
     cpu = None
     if rank == 0 and not args.no_cpu:
@@ -348,31 +376,62 @@ def main():
 
 
 def extra_gap_fill(torch, auvi, dev, stream, peak):
-    """BASELINE configs[4] scaled to one GPU: 16384^2 FP32 at 70 % mask, full-grid gap fill."""
-    n = 16384
+    """BASELINE configs[4] on one GPU: FP32 grid at 70 % mask, full-grid gap fill -- every method at 16384^2 and
+    the IDW headline of that config at the full 65536^2 (17.2 GB in + 17.2 GB out on one B200)."""
     res = {}
-    z = synth_grid_device(torch, n, n, 0, n, dev)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(42)
-    mask = torch.rand((n, n), device=dev, generator=gen) < 0.70
-    z[mask] = float("nan")
-    del mask
-    g = auvi.Grid(adopt=dict(ptr=z.data_ptr(), dtype=auvi.F32, n_lat=n, n_lon=n, ld=n, row0=0, rows=n, keep=z),
-                  min_lon=100.0, max_lon=110.0, min_lat=-10.0, max_lat=0.0, device=dev.index)
-    out = torch.empty((n, n), dtype=torch.float32, device=dev)
-    for name, meth in (("idw", auvi.IDW), ("nn", auvi.NN), ("kriging", auvi.KRIGING), ("nearest4_mean(cubic fallback)", auvi.CUBIC)):
-        fn = lambda: g.lattice_device(meth, auvi.AXIS_NODES, 1, 1, 1, 0, n, out.data_ptr(), n, None, stream)
-        fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(3):
+    for n, methods in ((16384, (("idw", auvi.IDW), ("nn", auvi.NN), ("kriging", auvi.KRIGING),
+                                ("nearest4_mean(cubic fallback)", auvi.CUBIC))), (65536, (("idw", auvi.IDW),))):
+        z = synth_grid_device(torch, n, n, 0, n, dev)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(42)
+        rows_per = 4096                                      # mask in row blocks: torch.rand of 65536^2 would need 17 GB more
+        for r in range(0, n, rows_per):
+            m = torch.rand((min(rows_per, n - r), n), device=dev, generator=gen) < 0.70
+            z[r:r + rows_per][m] = float("nan")
+            del m
+        g = auvi.Grid(adopt=dict(ptr=z.data_ptr(), dtype=auvi.F32, n_lat=n, n_lon=n, ld=n, row0=0, rows=n, keep=z),
+                      min_lon=100.0, max_lon=110.0, min_lat=-10.0, max_lat=0.0, device=dev.index)
+        out = torch.empty((n, n), dtype=torch.float32, device=dev)
+        for name, meth in methods:
+            fn = lambda: g.lattice_device(meth, auvi.AXIS_NODES, 1, 1, 1, 0, n, out.data_ptr(), n, None, stream)
             fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 3
-        res[f"gap_fill_70pct_{name}_16384sq_f32"] = {"Mcells_per_s": n * n / (ms * 1e-3) / 1e6, "ms": ms,
-                                                      "hbm_frac": 8.0 * n * n / (ms * 1e-3) / 1e9 / peak}
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            res[f"gap_fill_70pct_{name}_{n}sq_f32"] = {"Mcells_per_s": n * n / (ms * 1e-3) / 1e6, "ms": ms,
+                                                        "hbm_frac": 8.0 * n * n / (ms * 1e-3) / 1e9 / peak,
+                                                        "nan_left": int(torch.isnan(out).sum().item())}
+        g.close()
+        del z, out
+        torch.cuda.empty_cache()
+    return res
+
+
+def extra_grid_a_points(torch, auvi, local):
+    """The reference's Grid-A benchmark row (results/grid_A_runtimes_averaged.csv:8): 5,000,000 random query points
+    on the 4000 x 3200 synthetic grid through the Point-list API with host buffers (what GridD::batch* calls)."""
+    from oracle import binding as ob          # synthetic-field generator only
+    z = ob.synth_grid(3200, 4000, csv_round=False)
+    g = auvi.Grid(z, *BOUNDS, device=local)
+    rng = np.random.RandomState(1)
+    n = 5_000_000
+    pts = np.zeros((n, 3))
+    pts[:, 0] = rng.uniform(BOUNDS[0], BOUNDS[1], n)
+    pts[:, 1] = rng.uniform(BOUNDS[2], BOUNDS[3], n)
+    res = {}
+    for name, meth in (("bilinear", auvi.BILINEAR), ("cubic", auvi.CUBIC), ("kriging", auvi.KRIGING)):
+        g.interp_points(meth, pts)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            g.interp_points(meth, pts)
+        dt = (time.perf_counter() - t0) / 3
+        res[f"grid_a_5M_random_points_{name}"] = {"Mpts_per_s_e2e": n / dt / 1e6, "ms_e2e": dt * 1e3,
+                                                  "kernel_ms": g.last_kernel_ms}
     g.close()
     return res
 

@@ -48,7 +48,8 @@ int auvi_grid_adopt(const void* dev_rows, int dtype, int64_t n_lat, int64_t n_lo
                     double min_lon, double max_lon, double min_lat, double max_lat,
                     int device, auvi_grid** out);
 
-int auvi_grid_destroy(auvi_grid* g);      /* idempotent on NULL */
+int auvi_grid_destroy(auvi_grid* g);      /* idempotent on NULL; large device blocks go to a process-wide cache */
+int auvi_trim(void);                      /* release the cached device blocks (up to 6 GiB are kept for reuse) */
 
 /* ---- Point-list mode: replaces GridD::batch{Bilinear,Cubic,OrdinaryKriging}Interpolate
  *      (src/GridD.cu:95-150,156-193,199-236) and the three kernels of src/kernels.cu:173-546 ---- */
