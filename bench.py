@@ -173,8 +173,8 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)   # 0.56 s timed region: several clock samples under load
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the informational per-method table")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -351,6 +351,32 @@ def main():
             extra.update(extra_gap_fill(torch, auvi, dev, stream, peak))
             extra.update(extra_mariana(torch, auvi, local))
             extra.update(extra_grid_a_points(torch, auvi, local))
+            extra.update(extra_grid_a_lattice(torch, auvi, dev, stream, peak))
+
+    # ---- N > 1: the only collective on the path -- gathering output shards to one consumer (not in `value`) ----
+    gather = None
+    if dist is not None:
+        g_rows = min(my_rows, (4 << 30) // (out_ld * 4))            # bounded: at most 4 GiB per rank
+        sendbuf = out[:g_rows]
+        recv = [torch.empty_like(sendbuf) for _ in range(world)] if rank == 0 else None
+        dist.gather(sendbuf, recv, dst=0)                             # warm-up (NCCL over NVLink)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.gather(sendbuf, recv, dst=0)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        g_ms = float(t.item())
+        g_bytes = g_rows * out_ld * 4 * (world - 1)
+        gather = {"api": "torch.distributed.gather (NCCL)", "rows_per_rank": g_rows, "bytes_into_root": g_bytes, "ms": g_ms,
+                  "GBps_into_root": g_bytes / (g_ms * 1e-3) / 1e9,
+                  "full_gather_ms_estimate": g_ms * my_rows / g_rows,
+                  "Mcells_per_s_gathered_to_root_estimate": cells_total / ((ms_step + g_ms * my_rows / g_rows) * 1e-3) / 1e6}
+        if rank == 0:
+            assert torch.equal(recv[0], sendbuf)
+        del recv
 
     cpu = None
     if rank == 0 and not args.no_cpu:
@@ -368,7 +394,7 @@ def main():
                            "out_cells_per_gpu": cells_rank, "parallelism": f"row-sharded x{world}, halo {halo} rows, no collective",
                            "l2_policy": "inputs (1.07 GB) and outputs (17.2 GB) per step exceed the 126 MB L2"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-                "extra": extra}
+                "gather": gather, "extra": extra}
         print(json.dumps(line), flush=True)
     g.close()
     if dist is not None:
@@ -432,6 +458,34 @@ def extra_grid_a_points(torch, auvi, local):
         dt = (time.perf_counter() - t0) / 3
         res[f"grid_a_5M_random_points_{name}"] = {"Mpts_per_s_e2e": n / dt / 1e6, "ms_e2e": dt * 1e3,
                                                   "kernel_ms": g.last_kernel_ms}
+    g.close()
+    return res
+
+
+def extra_grid_a_lattice(torch, auvi, dev, stream, peak):
+    """BASELINE configs[0] at the generator's shipped size: the 4000 x 3200 FP64 Grid A, 2x expanded lattice
+    (7999 x 6399 = 51.2 M cells, test_interpolation.cpp:283-297), device-resident, every method."""
+    from oracle import binding as ob          # synthetic-field generator only
+    z = torch.from_numpy(ob.synth_grid(3200, 4000, csv_round=False)).to(dev)
+    g = auvi.Grid(adopt=dict(ptr=z.data_ptr(), dtype=auvi.F64, n_lat=3200, n_lon=4000, ld=4000, row0=0, rows=3200, keep=z),
+                  min_lon=BOUNDS[0], max_lon=BOUNDS[1], min_lat=BOUNDS[2], max_lat=BOUNDS[3], device=dev.index)
+    rows, cols = g.lattice_dims(auvi.AXIS_EXPANDED, 2, 2)
+    out = torch.empty((rows, 8000), dtype=torch.float64, device=dev)
+    res = {}
+    for name, meth in (("bilinear", auvi.BILINEAR), ("cubic", auvi.CUBIC), ("kriging", auvi.KRIGING), ("nn", auvi.NN),
+                       ("idw", auvi.IDW)):
+        fn = lambda: g.lattice_device(meth, auvi.AXIS_EXPANDED, 2, 2, 0, 0, rows, out.data_ptr(), 8000, None, stream)
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        res[f"grid_a_2x_lattice_f64_{name}"] = {"Mcells_per_s": rows * cols / (ms * 1e-3) / 1e6, "ms": ms,
+                                                 "hbm_frac": 10.0 * rows * cols / (ms * 1e-3) / 1e9 / peak}
     g.close()
     return res
 
