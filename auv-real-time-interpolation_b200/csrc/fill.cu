@@ -39,10 +39,30 @@ constexpr int kFHalo = 12;
 constexpr int kFBW = kFW + 2 * kFHalo;         // 88
 constexpr int kFBH = kFH + 2 * kFHalo;         // 56
 constexpr int kFThreads = 256;
-constexpr int kFNMax = 12;                     // per-thread candidate list capacity (longer lists: literal path)
+constexpr int kFCells = kFW * kFH;
+constexpr int kFPer = kFCells / kFThreads;     // queries per thread when every cell is masked
+constexpr int kFNMax = 13;                     // per-thread candidate list capacity of the general path (3 + a full ring-2 row pass)
 constexpr int kFRedoMax = 128;
 constexpr int kFSq = 3;                        // squared-offset tables cover |offset| <= kFSq
-constexpr int kFBins = 80;                     // (termination code 0..6) x (candidate count class 0..9) + spare
+constexpr int kFNear = 8;                      // near path: at most this many candidates, all within the 5 x 5 block
+constexpr int kFBinNear = 80;                  // bins 0..79: general path (termination x count); 80..84: near path by count
+constexpr int kFBins = 96;
+
+// 5 x 5 block around the search centre as one word whose bit order IS the reference's enumeration order
+// (GridH.cpp:36-117): bit 0 the centre; 1..6 ring-1 top/bottom rows (per column left to right: top, bottom);
+// 7..8 ring-1 left/right; 9..18 ring-2 top/bottom rows; 19..24 ring-2 left/right (per row top to bottom: left,
+// right).  The cells the reference has visited at each of its `count >= 4` checks are then the low 7 / 9 / 19 / 25
+// bits, and find-first-set walks the candidates in list order.
+__host__ __device__ constexpr int near_pos(int dy, int dx) {
+    return (dy == 0 && dx == 0) ? 0
+         : (dy == -1 || dy == 1) && dx >= -1 && dx <= 1 ? 1 + 2 * (dx + 1) + (dy > 0)
+         : (dy == 0 && (dx == -1 || dx == 1)) ? 7 + (dx > 0)
+         : (dy == -2 || dy == 2) ? 9 + 2 * (dx + 2) + (dy > 0)
+         : 19 + 2 * (dy + 1) + (dx > 0);
+}
+constexpr uint32_t kC1 = 0x7Fu, kC2 = 0x1FFu, kC3 = 0x7FFFFu, kC4 = 0x1FFFFFFu;
+
+constexpr double kSafeRatio = 1.0 - 8.8817841970012523e-16;   // 1 - 2^-50: a gap that sqrt rounding cannot close
 
 struct FillAxis {
     const double* coord;
@@ -64,20 +84,28 @@ struct FillParams {
 template <typename T>
 struct FillSmem {
     alignas(128) T tile[kFBH * kFBW];
-    double d2[kFNMax * kFThreads];            // per-thread candidate lists: squared distances
+    double d2[kFNMax * kFThreads];            // general path: per-thread candidate lists, squared distances.  Before the
+                                              // general path runs, its first 8 KB hold two queues (see the kernel)
     double sqx[kFW * (2 * kFSq + 1)];         // ((cx + d + 0.5) - x)^2 per tile column, d = -kFSq..kFSq
     double sqy[kFH * (2 * kFSq + 1)];
     double x[kFW], y[kFH];
-    uint32_t sorted[kFW * kFH];               // queries ordered by (termination, candidate count)
+    uint32_t rec[kFCells];                    // query records, ordered by bin after the scatter
     uint32_t mask[kFBH * 4];
+    uint32_t lut[5 * 32];                     // 5-bit row window of block row dy+2 -> its bits in enumeration order
+    uint32_t cell_off[32];                    // enumeration position -> byte offsets into the sqx / sqy rows: x | y << 16
+    int cell_tile[32];                        // enumeration position -> tile offset dy*kFBW + dx
+    int cell_dxy[32];                         // enumeration position -> (dx & 0xffff) | dy << 16
     int cx[kFW], cy[kFH];
     int hist[kFBins];
-    uint16_t code[kFNMax * kFThreads];        // per-thread candidate lists: packed (dy,dx) offsets
-    uint16_t queue[kFW * kFH];
+    uint16_t code[kFNMax * kFThreads];        // general path: per-thread candidate lists, packed (dy,dx) offsets
+    uint16_t reck[kFCells];                   // cell (lj*kFW + li) of each record
     uint16_t redo[kFRedoMax];
-    int qn, rn;
+    int qn, rn, dn, tn, q_near;
     uint64_t bar;
 };
+
+static_assert(sizeof(FillSmem<float>) <= 75 * 1024, "three CTAs per SM need <= 75 KB each (f32 grids)");
+static_assert(sizeof(FillSmem<double>) <= 113 * 1024, "two CTAs per SM (f64 grids)");
 
 template <typename T, int METHOD>
 __device__ __noinline__ T fill_cell_literal(const FillParams<T>* p, int64_t J, int I) {
@@ -89,6 +117,160 @@ __device__ __noinline__ T fill_cell_literal(const FillParams<T>* p, int64_t J, i
 __device__ __forceinline__ double sq_offset(double cf, int d, double q) {
     const double t = dsub(dadd(cf, __int2double_rn(d)), q);
     return dmul(t, t);
+}
+
+__device__ __forceinline__ float rcp_sfu(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// ---- helper: selection in registers ------------------------------------------------------------------------------
+// The reference's partial selection sort with swaps (GridH.cpp:123-140) on a list of N (distance, cell) pairs held
+// in registers: pass m finds the FIRST strict minimum of entries m..N-1 and swaps it with entry m.  Cells are
+// distinct, so the winner is recognised by its cell and the swap is spelled with selects: no register is indexed
+// dynamically.  Unused tail entries hold +inf and never win.
+template <int N, int PASSES>
+__device__ __forceinline__ void select_in_registers(double (&d)[N], int (&c)[N]) {
+#pragma unroll
+    for (int m = 0; m < PASSES && m + 1 < N; ++m) {
+        double dbest = d[m];
+        int cbest = c[m];
+#pragma unroll
+        for (int k = m + 1; k < N; ++k) {
+            const bool lt = d[k] < dbest;
+            dbest = lt ? d[k] : dbest; cbest = lt ? c[k] : cbest;
+        }
+#pragma unroll
+        for (int k = m + 1; k < N; ++k) {
+            const bool here = c[k] == cbest;
+            d[k] = here ? d[m] : d[k]; c[k] = here ? c[m] : c[k];
+        }
+        d[m] = dbest; c[m] = cbest;
+    }
+}
+
+// ---- helper: ordinary kriging on four picks, out of line ---------------------------------------------------------------
+// One copy of the FP64 system assembly + solve (exact.cuh, GridH.cpp:361-419) shared by every call site, with its own
+// register allocation: inlined into each list-length variant of the near path it cost the whole kernel spills.
+template <typename T>
+__device__ __noinline__ double kriging_four(const GridView<T>* g, int i0, int i1, int i2, int i3, int j0, int j1, int j2,
+                                            int j3, double v0, double v1, double v2, double v3, double lon, double lat) {
+    Picked pk;
+    pk.found = 4;
+    pk.i[0] = i0; pk.i[1] = i1; pk.i[2] = i2; pk.i[3] = i3;
+    pk.j[0] = j0; pk.j[1] = j1; pk.j[2] = j2; pk.j[3] = j3;
+    pk.v[0] = v0; pk.v[1] = v1; pk.v[2] = v2; pk.v[3] = v3;
+    pk.d[0] = pk.d[1] = pk.d[2] = pk.d[3] = 0.0;
+    return kriging_from_picked(*g, pk, lon, lat);
+}
+
+// ---- helper: the method's value from four picks ---------------------------------------------------------------------
+// v = the picks' values in selection order, d2 = their SQUARED index-space distances (> 0), (pi,pj) their global cells.
+template <typename T, int METHOD>
+__device__ __forceinline__ T finish_four(const FillParams<T>& p, const T (&v)[4], const double (&d2)[4], const int (&pi)[4],
+                                         const int (&pj)[4], int I, int64_t J) {
+    if (METHOD == NN) return v[0];
+    if (METHOD == CUBIC) {
+        // fallbackAverage (GridH.cpp:10-18) of four numbers: ((0 + a) + b + c + d) / 4
+        const double sum = dadd(dadd(dadd(dadd(0.0, static_cast<double>(v[0])), static_cast<double>(v[1])),
+                                     static_cast<double>(v[2])), static_cast<double>(v[3]));
+        return static_cast<T>(ddiv(sum, 4.0));
+    }
+    if (METHOD == IDW) {
+        // FP32 weights 1/d^2 through the SFU reciprocal; values centred on the first pick
+        if (d2[0] == 0.0) return v[0];                               // on a cell centre (picks are in ascending order)
+        float num = 0.f, den = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float w = rcp_sfu(static_cast<float>(d2[e]));
+            if (e) num = fmaf(w, static_cast<float>(v[e] - v[0]), num);
+            den += w;
+        }
+        return static_cast<T>(v[0] + static_cast<T>(__fdividef(num, den)));
+    }
+    return static_cast<T>(kriging_four<T>(&p.g, pi[0], pi[1], pi[2], pi[3], pj[0], pj[1], pj[2], pj[3], static_cast<double>(v[0]),
+                                          static_cast<double>(v[1]), static_cast<double>(v[2]), static_cast<double>(v[3]),
+                                          __ldg(p.lon.coord + I), __ldg(p.lat.coord + J)));
+}
+
+// ---- helper: fewer than four candidates (the search ran out of rings) -------------------------------------------------
+template <typename T, int METHOD>
+__device__ __noinline__ T finish_few(int cnt, double v0, double v1, double v2, double d0, double d1, double d2) {
+    Picked pk;
+    pk.found = cnt;
+    pk.v[0] = v0; pk.v[1] = v1; pk.v[2] = v2; pk.v[3] = qnan();
+    pk.d[0] = d0; pk.d[1] = d1; pk.d[2] = d2; pk.d[3] = qnan();
+    if (cnt == 0) return static_cast<T>(qnan());
+    if (METHOD == NN) return static_cast<T>(pk.v[0]);              // the caller ran the first-minimum pass
+    if (METHOD == IDW) {
+        float num = 0.f, den = 0.f;
+        for (int e = 0; e < cnt; ++e) {
+            if (pk.d[e] == 0.0) return static_cast<T>(pk.v[e]);
+            const float w = rcp_sfu(static_cast<float>(pk.d[e]));
+            num = fmaf(w, static_cast<float>(pk.v[e] - pk.v[0]), num);
+            den += w;
+        }
+        return static_cast<T>(pk.v[0] + static_cast<double>(__fdividef(num, den)));
+    }
+    return static_cast<T>(mean_found(pk));                          // CUBIC and KRIGING: GridH.cpp:291-298, :350-356
+}
+
+// ---- helper: one near-path query ---------------------------------------------------------------------------------------
+// The candidates are the set bits of `cand`, in list order; their squared distances come from the per-tile tables
+// (same operations as GridH.cpp:42-44).  The selection runs on squared distances (REPLAY = false): sqrt is monotone,
+// so a pass can only come out differently if a remaining value lies above the pass minimum by less than sqrt
+// rounding can close.  That is checked on the sorted chain afterwards; such a query returns false and is replayed
+// with REPLAY = true, which takes the square roots first -- the reference's own comparison, bit for bit.
+template <typename T, int METHOD, int N, bool REPLAY>
+__device__ __forceinline__ bool near_query(const FillSmem<T>& s, const FillParams<T>& p, uint32_t cand, int k, int c0,
+                                           int r0, int I0, int64_t J0, T* out_tile) {
+    constexpr int kPasses = METHOD == NN ? 1 : 4;
+    const int lj = k / kFW, li = k % kFW;
+    const char* const sqx = reinterpret_cast<const char*>(s.sqx + li * (2 * kFSq + 1) + kFSq - 2);   // [dx + 2]
+    const char* const sqy = reinterpret_cast<const char*>(s.sqy + lj * (2 * kFSq + 1) + kFSq - 2);
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double d[N];
+    int c[N];
+#pragma unroll
+    for (int e = 0; e < N; ++e) {
+        const bool has = cand != 0u;
+        const int b = (__ffs(cand) - 1) & 31;                      // exhausted list: cell 31, overwritten by +inf
+        cand &= cand - 1u;
+        const uint32_t off = s.cell_off[b];
+        double v = dadd(*reinterpret_cast<const double*>(sqx + (off & 0xffffu)),
+                        *reinterpret_cast<const double*>(sqy + (off >> 16)));
+        if (REPLAY) v = dsqrt(v);                                   // GridH.cpp:44
+        d[e] = has ? v : inf;
+        c[e] = b;
+    }
+    select_in_registers<N, kPasses>(d, c);
+    if (!REPLAY) {
+        // smallest value left behind that is strictly above the last pick, then the chain of picks
+        double rest = inf;
+#pragma unroll
+        for (int e = kPasses; e < N; ++e) rest = (d[e] > d[kPasses - 1] && d[e] < rest) ? d[e] : rest;
+        bool tie = d[kPasses - 1] != rest && dmul(rest, kSafeRatio) < d[kPasses - 1];
+#pragma unroll
+        for (int e = 0; e + 1 < kPasses; ++e) tie |= d[e] != d[e + 1] && dmul(d[e + 1], kSafeRatio) < d[e];
+        if (tie) return false;
+    }
+    const int cig = s.cx[li], cjg = s.cy[lj];
+    const T* const centre = s.tile + (cjg - r0) * kFBW + (cig - c0);
+    T v[4];
+    double d2[4];
+    int pi[4], pj[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        v[e] = centre[s.cell_tile[c[e]]];
+        d2[e] = REPLAY ? dmul(d[e], d[e]) : d[e];
+        if (METHOD == KRIGING) {
+            const int dxy = s.cell_dxy[c[e]];
+            pi[e] = cig + static_cast<int16_t>(dxy & 0xffff); pj[e] = cjg + (dxy >> 16);
+        } else { pi[e] = 0; pj[e] = 0; }
+    }
+    __stcs(out_tile + lj * p.out_ld + li, finish_four<T, METHOD>(p, v, d2, pi, pj, I0 + li, J0 + lj));
+    return true;
 }
 
 template <typename T, int METHOD>
@@ -103,9 +285,27 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     const int c0 = I0 - kFHalo;                                   // 16-byte aligned for f32 and f64
     const int r0 = static_cast<int>(J0) - kFHalo;
     T* const out_tile = p.out + (J0 - p.row_begin) * p.out_ld + I0;
+    // two queues live in the general path's list storage until that path starts:
+    uint16_t* const queue = reinterpret_cast<uint16_t*>(s.d2);     // masked cells of the tile, compacted (read by phase A1)
+    uint16_t* const defer = queue + kFCells;                       // A1 -> A2: queries the 5 x 5 block cannot decide;
+                                                                   // near path -> replay: queries with a near tie
 
-    if (tid == 0) { s.qn = 0; s.rn = 0; }
+    if (tid == 0) { s.qn = 0; s.rn = 0; s.dn = 0; s.tn = 0; }
     if (tid < kFBins) s.hist[tid] = 0;
+    if (tid < 5 * 32) {
+        const int dy = tid / 32 - 2, w = tid & 31;
+        uint32_t v = 0;
+#pragma unroll
+        for (int dx = -2; dx <= 2; ++dx) if ((w >> (dx + 2)) & 1) v |= 1u << near_pos(dy, dx);
+        s.lut[tid] = v;
+    } else if (tid < 6 * 32) {
+        const int b = tid - 5 * 32;                                 // cells 25..31 are never looked up; keep them harmless
+        const int dy = b < 25 ? b / 5 - 2 : 0, dx = b < 25 ? b % 5 - 2 : 0;
+        const int pos = b < 25 ? near_pos(dy, dx) : b;
+        s.cell_off[pos] = static_cast<uint32_t>((dx + 2) * 8) | (static_cast<uint32_t>((dy + 2) * 8) << 16);
+        s.cell_tile[pos] = dy * kFBW + dx;
+        s.cell_dxy[pos] = (dx & 0xffff) | (dy << 16);
+    }
     if (p.use_tma) {
         if (tid == 0) { prefetch_tmap(&tmap); mbar_init(&s.bar, 1); }
         __syncthreads();
@@ -172,7 +372,7 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 
     // ---- pass valid cells through (coalesced), compact masked cells into the queue -------------------------
 #pragma unroll
-    for (int it = 0; it < kFW * kFH / kFThreads; ++it) {
+    for (int it = 0; it < kFPer; ++it) {
         const int k = it * kFThreads + tid;
         const int lj = k / kFW, li = k % kFW;
         const bool in_range = (J0 + lj < p.row_end) && (I0 + li < W);
@@ -184,108 +384,170 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         int base = 0;
         if (lane == 0 && m) base = atomicAdd(&s.qn, __popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (todo) s.queue[base + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(k);
+        if (todo) queue[base + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(k);
     }
     __syncthreads();
 
-    // ---- phase A: where does each query's search stop, and with how many candidates? ------------------------
-    // (GridH.cpp:48-117: the count is checked after each top/bottom pass and after each left/right pass.)
-    // Queries are then ORDERED by (termination ring/pass, candidate count) so that the warps of phase B run
-    // the same ring code and the same list lengths: the data-dependent loops stop diverging.
-    const int qn = s.qn;
     auto window = [&](int row, int wi, int sh) -> uint32_t {       // validity of columns ci-10..ci+10 of a tile row
         return __funnelshift_r(s.mask[row * 4 + wi], s.mask[row * 4 + wi + 1], sh) & 0x1FFFFFu;
     };
+    auto to_literal = [&](int k) {                                  // hand a query to the literal per-query path
+        const int slot = atomicAdd(&s.rn, 1);
+        if (slot < kFRedoMax) s.redo[slot] = static_cast<uint16_t>(k);
+        else __stcs(out_tile + (k / kFW) * p.out_ld + (k % kFW), fill_cell_literal<T, METHOD>(&p, J0 + k / kFW, I0 + k % kFW));
+    };
+
+    // ---- phase A1: the 5 x 5 block around each query's centre decides most searches ---------------------------
+    // (GridH.cpp:48-117: the count is checked after each top/bottom pass and after each left/right pass.)  A query
+    // whose search ends inside the block with at most kFNear candidates takes the near path: its record is the set
+    // of candidate cells.  The others are deferred to the general termination scan (phase A2).
+    const int qn = s.qn;
     for (int q = tid; q < qn; q += kFThreads) {
-        const int k = s.queue[q];
+        const int k = queue[q];
         const int lj = k / kFW, li = k % kFW;
-        uint32_t rec = 0xffffffffu;                                // "not for phase B"
+        uint32_t rec = 0xffffffffu;                                // "no record"
         if (isnan(s.x[li]) || isnan(s.y[lj])) {
             __stcs(out_tile + lj * p.out_ld + li, static_cast<T>(qnan()));   // query out of bounds
         } else {
             const int ci = s.cx[li] - c0, cj = s.cy[lj] - r0;       // search centre in tile coordinates
-            bool literal = (ci < 11) | (ci > kFBW - 12) | (cj < 11) | (cj > kFBH - 12);   // never for node queries
-            if (!literal) {
-                const int sh0 = ci - 10, wi = sh0 >> 5, sh = sh0 & 31;
-                uint32_t wt[kMaxRadius + 1], wb[kMaxRadius + 1];
-                const uint32_t w0 = window(cj, wi, sh);
-                wt[0] = w0; wb[0] = w0;
-                int n = (w0 >> 10) & 1;
-                int r_end = kMaxRadius, lr_end = 1;                 // last ring visited; did its left/right pass run?
-                bool done = false;
+            if ((ci < 11) | (ci > kFBW - 12) | (cj < 11) | (cj > kFBH - 12)) to_literal(k);   // never for node queries
+            else {
+                const int sh0 = ci - 2, wi = sh0 >> 5, sh = sh0 & 31;
+                uint32_t blk = 0;
 #pragma unroll
-                for (int r = 1; r <= kMaxRadius; ++r) {
-                    if (!done) {
-                        wt[r] = window(cj - r, wi, sh); wb[r] = window(cj + r, wi, sh);
-                        const uint32_t tbm = ((2u << (2 * r)) - 1u) << (10 - r);
-                        n += __popc(wt[r] & tbm) + __popc(wb[r] & tbm);
-                        if (n >= 4) { done = true; r_end = r; lr_end = 0; }
-                        else {
-                            const uint32_t lrm = (1u << (10 - r)) | (1u << (10 + r));
-                            int c = __popc(w0 & lrm);
-#pragma unroll
-                            for (int d = 1; d < r; ++d) c += __popc(wt[d] & lrm) + __popc(wb[d] & lrm);
-                            n += c;
-                            if (n >= 4) { done = true; r_end = r; lr_end = 1; }
-                        }
-                    }
+                for (int dy = -2; dy <= 2; ++dy) {
+                    const uint32_t* mrow = s.mask + (cj + dy) * 4 + wi;
+                    blk |= s.lut[(dy + 2) * 32 + (__funnelshift_r(mrow[0], mrow[1], sh) & 31u)];
                 }
-                if (n > kFNMax) literal = true;
-                else {
-                    const int tcode = r_end <= 3 ? (r_end - 1) * 2 + lr_end : 6;
-                    const int ncls = n < 4 ? 9 : n - 4;             // n in 4..12 -> 0..8
-                    const int bin = tcode * 10 + ncls;
+                const int n1 = __popc(blk & kC1), n2 = __popc(blk & kC2), n3 = __popc(blk & kC3), n4 = __popc(blk);
+                const uint32_t cm = n1 >= 4 ? kC1 : (n2 >= 4 ? kC2 : (n3 >= 4 ? kC3 : kC4));
+                const int n = n1 >= 4 ? n1 : (n2 >= 4 ? n2 : (n3 >= 4 ? n3 : n4));
+                if (n >= 4 && n <= kFNear) {
+                    const int bin = kFBinNear + n - 4;
                     atomicAdd(&s.hist[bin], 1);
-                    rec = static_cast<uint32_t>(k) | (static_cast<uint32_t>(r_end) << 12) |
-                          (static_cast<uint32_t>(lr_end) << 16) | (static_cast<uint32_t>(n) << 17) |
-                          (static_cast<uint32_t>(bin) << 22);
+                    rec = (blk & cm) | (static_cast<uint32_t>(bin) << 25);
+                } else {
+                    defer[atomicAdd(&s.dn, 1)] = static_cast<uint16_t>(q);
                 }
-            }
-            if (literal) {
-                const int slot = atomicAdd(&s.rn, 1);
-                if (slot < kFRedoMax) s.redo[slot] = static_cast<uint16_t>(k);
-                else __stcs(out_tile + lj * p.out_ld + li, fill_cell_literal<T, METHOD>(&p, J0 + lj, I0 + li));
             }
         }
-        s.sorted[q] = rec;                                          // parked here until the scatter below
+        s.rec[q] = rec; s.reck[q] = static_cast<uint16_t>(k);
     }
     __syncthreads();
+    // ---- phase A2: general termination scan (rings up to radius 10) for the deferred queries ---------------
+    const int dn = s.dn;
+    for (int t = tid; t < dn; t += kFThreads) {
+        const int q = defer[t];
+        const int k = s.reck[q];
+        const int lj = k / kFW, li = k % kFW;
+        const int ci = s.cx[li] - c0, cj = s.cy[lj] - r0;
+        const int sh0 = ci - 10, wi = sh0 >> 5, sh = sh0 & 31;
+        uint32_t wt[kMaxRadius + 1], wb[kMaxRadius + 1];
+        const uint32_t w0 = window(cj, wi, sh);
+        wt[0] = w0; wb[0] = w0;
+        int n = (w0 >> 10) & 1;
+        int r_end = kMaxRadius, lr_end = 1;                         // last ring visited; did its left/right pass run?
+        bool done = false;
+#pragma unroll
+        for (int r = 1; r <= kMaxRadius; ++r) {
+            if (!done) {
+                wt[r] = window(cj - r, wi, sh); wb[r] = window(cj + r, wi, sh);
+                const uint32_t tbm = ((2u << (2 * r)) - 1u) << (10 - r);
+                n += __popc(wt[r] & tbm) + __popc(wb[r] & tbm);
+                if (n >= 4) { done = true; r_end = r; lr_end = 0; }
+                else {
+                    const uint32_t lrm = (1u << (10 - r)) | (1u << (10 + r));
+                    int c = __popc(w0 & lrm);
+#pragma unroll
+                    for (int d = 1; d < r; ++d) c += __popc(wt[d] & lrm) + __popc(wb[d] & lrm);
+                    n += c;
+                    if (n >= 4) { done = true; r_end = r; lr_end = 1; }
+                }
+            }
+        }
+        if (n > kFNMax) to_literal(k);
+        else {
+            const int tcode = r_end <= 3 ? (r_end - 1) * 2 + lr_end : 6;
+            const int ncls = n < 4 ? 9 : n - 4;                     // n in 4..12 -> 0..8
+            const int bin = tcode * 10 + ncls;
+            atomicAdd(&s.hist[bin], 1);
+            s.rec[q] = static_cast<uint32_t>(r_end) | (static_cast<uint32_t>(lr_end) << 4) |
+                       (static_cast<uint32_t>(n) << 5) | (static_cast<uint32_t>(bin) << 25);
+        }
+    }
+    __syncthreads();
+    // ---- order the records by bin: the warps of phase B then run the same code on lists of the same length ----
     if (warp == 0) {                                               // exclusive scan of the histogram
         int carry = 0;
+#pragma unroll
         for (int b0 = 0; b0 < kFBins; b0 += 32) {
             const int b = b0 + lane;
-            int v = b < kFBins ? s.hist[b] : 0;
+            const int v = s.hist[b];
             int incl = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += t;
             }
-            if (b < kFBins) s.hist[b] = carry + incl - v;
+            s.hist[b] = carry + incl - v;
+            if (b == kFBinNear) s.q_near = carry + incl - v;        // first near-path record
             carry += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (lane == 0) s.qn = carry;                               // queries that go to phase B
+        if (lane == 0) s.qn = carry;                               // records that go to phase B
     }
     __syncthreads();
-    // scatter: records move from the parking order to the bin order (read all, sync, then write)
-    uint32_t mine[kFW * kFH / kFThreads];
+    {   // scatter: records move from queue order to bin order (read all, sync, then write)
+        uint32_t mine[kFPer];
+        uint16_t minek[kFPer];
 #pragma unroll
-    for (int it = 0; it < kFW * kFH / kFThreads; ++it) {
-        const int q = it * kFThreads + tid;
-        mine[it] = q < qn ? s.sorted[q] : 0xffffffffu;
+        for (int it = 0; it < kFPer; ++it) {
+            const int q = it * kFThreads + tid;
+            mine[it] = q < qn ? s.rec[q] : 0xffffffffu;
+            minek[it] = q < qn ? s.reck[q] : 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < kFPer; ++it) {
+            if (mine[it] != 0xffffffffu) {
+                const int dst = atomicAdd(&s.hist[mine[it] >> 25], 1);
+                s.rec[dst] = mine[it]; s.reck[dst] = minek[it];
+            }
+        }
     }
     __syncthreads();
-#pragma unroll
-    for (int it = 0; it < kFW * kFH / kFThreads; ++it) {
-        if (mine[it] != 0xffffffffu) s.sorted[atomicAdd(&s.hist[mine[it] >> 22], 1)] = mine[it];
+    const int qb = s.qn, q_near = s.q_near;
+
+    // ---- phase B, near path: one thread per query, candidate list and selection in registers ---------------------
+    // The bins are ordered by candidate count, so a warp's queries have (nearly) the same count: the list length
+    // is a compile-time constant chosen per warp.
+    for (int base = q_near; base < qb; base += kFThreads) {
+        const int q = base + tid;
+        const bool active = q < qb;
+        const uint32_t cand = active ? (s.rec[q] & kC4) : 0u;
+        const int nmax = __reduce_max_sync(0xffffffffu, __popc(cand));
+        if (nmax == 0) continue;
+        const int k = active ? s.reck[q] : 0;
+        if (!active) continue;
+        bool ok;
+        if (nmax <= 4) ok = near_query<T, METHOD, 4, false>(s, p, cand, k, c0, r0, I0, J0, out_tile);
+        else if (nmax <= 6) ok = near_query<T, METHOD, 6, false>(s, p, cand, k, c0, r0, I0, J0, out_tile);
+        else ok = near_query<T, METHOD, kFNear, false>(s, p, cand, k, c0, r0, I0, J0, out_tile);
+        if (!ok) defer[atomicAdd(&s.tn, 1)] = static_cast<uint16_t>(q);
+    }
+    __syncthreads();
+    // ---- phase B, replay of the near-path queries that met a near tie: the same selection on square-rooted distances ---
+    const int tn = s.tn;
+    for (int t = tid; t < tn; t += kFThreads) {
+        const int q = defer[t];
+        near_query<T, METHOD, kFNear, true>(s, p, s.rec[q] & kC4, s.reck[q], c0, r0, I0, J0, out_tile);
     }
     __syncthreads();
 
-    // ---- phase B: one thread per query, bin order ---------------------------------------------------------------
-    const int qb = s.qn;
-    for (int q = tid; q < qb; q += kFThreads) {
-        const uint32_t rec = s.sorted[q];
-        const int k = rec & 0xfff, r_end = (rec >> 12) & 15, lr_end = (rec >> 16) & 1, n = (rec >> 17) & 31;
+    // ---- phase B, general path: searches that leave the 5 x 5 block or hold more than kFNear candidates -------------
+    for (int q = tid; q < q_near; q += kFThreads) {
+        const uint32_t rec = s.rec[q];
+        const int k = s.reck[q];
+        const int r_end = rec & 15, lr_end = (rec >> 4) & 1, n = (rec >> 5) & 31;
         const int lj = k / kFW, li = k % kFW;
         const int cig = s.cx[li], cjg = s.cy[lj];
         const int ci = cig - c0, cj = cjg - r0;
@@ -351,16 +613,15 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         // -- the reference's partial selection sort with swaps (GridH.cpp:123-140) on squared distances.
         // NN only needs the first pick: pass 0 (with fewer than four candidates the oracle's "first strict
         // minimum" is the same scan); the other methods run the four passes when four candidates exist.
-        constexpr double kSafe = 1.0 - 8.8817841970012523e-16;      // 1 - 2^-50
         bool unsure = (cnt != n);
         const int n_pass = METHOD == NN ? (cnt > 0 ? 1 : 0) : (cnt >= 4 ? 4 : 0);
         for (int m = 0; m < n_pass; ++m) {
             int best = m;
             const double dm = ld2[m * kFThreads];
-            double dbest = dm, thr = dmul(dm, kSafe);
+            double dbest = dm, thr = dmul(dm, kSafeRatio);
             for (int kk = m + 1; kk < cnt; ++kk) {
                 const double dk = ld2[kk * kFThreads];
-                if (dk < thr) { best = kk; dbest = dk; thr = dmul(dk, kSafe); }
+                if (dk < thr) { best = kk; dbest = dk; thr = dmul(dk, kSafeRatio); }
                 else if (dk < dbest) unsure = true;                // within a few ulps: sqrt may tie
             }
             if (best != m) {
@@ -369,59 +630,33 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 lcode[m * kFThreads] = lcode[best * kFThreads]; lcode[best * kFThreads] = cm;
             }
         }
-        if (unsure) {
-            const int slot = atomicAdd(&s.rn, 1);
-            if (slot < kFRedoMax) s.redo[slot] = static_cast<uint16_t>(k);
-            else __stcs(out_tile + lj * p.out_ld + li, fill_cell_literal<T, METHOD>(&p, J0 + lj, I0 + li));
-            continue;
-        }
-        // -- gather the picks (first min(cnt,4) list entries) and finish the method
-        const int np = cnt < 4 ? cnt : 4;
-        Picked pk;
-        pk.found = cnt;
+        if (unsure) { to_literal(k); continue; }
+        if (cnt >= 4) {
+            T v[4];
+            double d2v[4];
+            int pi[4], pj[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if (e < np) {
+            for (int e = 0; e < 4; ++e) {
                 const int code = lcode[e * kFThreads];
                 const int dx = (code & 31) - 10, dy = (code >> 5) - 10;
-                pk.i[e] = cig + dx; pk.j[e] = cjg + dy;
-                pk.v[e] = static_cast<double>(s.tile[(cj + dy) * kFBW + ci + dx]);
-                pk.d[e] = ld2[e * kFThreads];                        // SQUARED distance
-            } else { pk.i[e] = -1; pk.j[e] = -1; pk.v[e] = qnan(); pk.d[e] = qnan(); }
-        }
-        double result;
-        if (METHOD == CUBIC) {
-            result = cnt < 4 ? mean_found(pk) : mean_valid4(pk.v[0], pk.v[1], pk.v[2], pk.v[3]);
-        } else if (METHOD == NN) {
-            result = cnt > 0 ? pk.v[0] : qnan();
-        } else if (METHOD == IDW) {
-            result = qnan();
-            if (cnt > 0) {
-                // FP32 weights 1/d^2 through the SFU reciprocal; values centred on the first pick
-                float num = 0.f, den = 0.f;
-                const double ref = pk.v[0];
-                bool hit = false;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if (e < np && !hit) {
-                        if (pk.d[e] == 0.0) { result = pk.v[e]; hit = true; }
-                        else {
-                            const float w = __frcp_rn(static_cast<float>(pk.d[e]));
-                            num = fmaf(w, static_cast<float>(pk.v[e] - ref), num);
-                            den += w;
-                        }
-                    }
-                }
-                if (!hit) result = ref + static_cast<double>(__fdividef(num, den));
+                v[e] = s.tile[(cj + dy) * kFBW + ci + dx];
+                d2v[e] = ld2[e * kFThreads];
+                pi[e] = cig + dx; pj[e] = cjg + dy;
             }
-        } else {   // KRIGING
-            if (cnt < 4) result = mean_found(pk);
-            else result = kriging_from_picked(p.g, pk, __ldg(p.lon.coord + I0 + li), __ldg(p.lat.coord + J0 + lj));
+            __stcs(out_tile + lj * p.out_ld + li, finish_four<T, METHOD>(p, v, d2v, pi, pj, I0 + li, J0 + lj));
+        } else {                                                    // the search ran out of rings (GridH.cpp:291-298)
+            double fv[3], fd[3];
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                const int code = e < cnt ? lcode[e * kFThreads] : (10 * 32 + 10);
+                fv[e] = static_cast<double>(s.tile[(cj + (code >> 5) - 10) * kFBW + ci + (code & 31) - 10]);
+                fd[e] = e < cnt ? ld2[e * kFThreads] : 0.0;
+            }
+            __stcs(out_tile + lj * p.out_ld + li, finish_few<T, METHOD>(cnt, fv[0], fv[1], fv[2], fd[0], fd[1], fd[2]));
         }
-        __stcs(out_tile + lj * p.out_ld + li, static_cast<T>(result));
     }
     __syncthreads();
-    // ---- queries the bitmask path handed back: literal per-query evaluation ---------------------------------
+    // ---- queries the bitmask paths handed back: literal per-query evaluation ---------------------------------
     const int rn = min(s.rn, kFRedoMax);
     for (int q = tid; q < rn; q += kFThreads) {
         const int k = s.redo[q];
