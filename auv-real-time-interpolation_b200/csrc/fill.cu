@@ -43,6 +43,7 @@ constexpr int kFCells = kFW * kFH;
 constexpr int kFPer = kFCells / kFThreads;     // queries per thread when every cell is masked
 constexpr int kFNMax = 13;                     // per-thread candidate list capacity of the general path (3 + a full ring-2 row pass)
 constexpr int kFRedoMax = 128;
+constexpr int kFReplayMax = 256;                // near-tie queries replayed with square roots (more: literal path)
 constexpr int kFSq = 3;                        // squared-offset tables cover |offset| <= kFSq
 constexpr int kFNear = 8;                      // near path: at most this many candidates, all within the 5 x 5 block
 constexpr int kFBinNear = 80;                  // bins 0..79: general path (termination x count); 80..84: near path by count
@@ -100,7 +101,8 @@ struct FillSmem {
     uint16_t code[kFNMax * kFThreads];        // general path: per-thread candidate lists, packed (dy,dx) offsets
     uint16_t reck[kFCells];                   // cell (lj*kFW + li) of each record
     uint16_t redo[kFRedoMax];
-    int qn, rn, dn, tn, q_near;
+    uint16_t replay[kFReplayMax];
+    int qn, rn, dn, tn, q_near, next;
     uint64_t bar;
 };
 
@@ -223,7 +225,7 @@ __device__ __noinline__ T finish_few(int cnt, double v0, double v1, double v2, d
 // rounding can close.  That is checked on the sorted chain afterwards; such a query returns false and is replayed
 // with REPLAY = true, which takes the square roots first -- the reference's own comparison, bit for bit.
 template <typename T, int METHOD, int N, bool REPLAY>
-__device__ __forceinline__ bool near_query(const FillSmem<T>& s, const FillParams<T>& p, uint32_t cand, int k, int c0,
+__device__ __forceinline__ bool near_query(FillSmem<T>& s, const FillParams<T>& p, uint32_t cand, int q, int k, int c0,
                                            int r0, int I0, int64_t J0, T* out_tile) {
     constexpr int kPasses = METHOD == NN ? 1 : 4;
     const int lj = k / kFW, li = k % kFW;
@@ -255,19 +257,21 @@ __device__ __forceinline__ bool near_query(const FillSmem<T>& s, const FillParam
         for (int e = 0; e + 1 < kPasses; ++e) tie |= d[e] != d[e + 1] && dmul(d[e + 1], kSafeRatio) < d[e];
         if (tie) return false;
     }
+    if (METHOD == KRIGING) {
+        // the FP64 system is solved in a phase of its own (kernel, "kriging of the near-path picks"): here only the
+        // picks are recorded, so the selection does not carry the solver's registers
+        s.rec[q] = static_cast<uint32_t>(c[0] | (c[1] << 5) | (c[2] << 10) | (c[3] << 15)) | (127u << 25);
+        return true;
+    }
     const int cig = s.cx[li], cjg = s.cy[lj];
     const T* const centre = s.tile + (cjg - r0) * kFBW + (cig - c0);
     T v[4];
     double d2[4];
-    int pi[4], pj[4];
+    const int pi[4] = {0, 0, 0, 0}, pj[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         v[e] = centre[s.cell_tile[c[e]]];
         d2[e] = REPLAY ? dmul(d[e], d[e]) : d[e];
-        if (METHOD == KRIGING) {
-            const int dxy = s.cell_dxy[c[e]];
-            pi[e] = cig + static_cast<int16_t>(dxy & 0xffff); pj[e] = cjg + (dxy >> 16);
-        } else { pi[e] = 0; pj[e] = 0; }
     }
     __stcs(out_tile + lj * p.out_ld + li, finish_four<T, METHOD>(p, v, d2, pi, pj, I0 + li, J0 + lj));
     return true;
@@ -287,10 +291,9 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     T* const out_tile = p.out + (J0 - p.row_begin) * p.out_ld + I0;
     // two queues live in the general path's list storage until that path starts:
     uint16_t* const queue = reinterpret_cast<uint16_t*>(s.d2);     // masked cells of the tile, compacted (read by phase A1)
-    uint16_t* const defer = queue + kFCells;                       // A1 -> A2: queries the 5 x 5 block cannot decide;
-                                                                   // near path -> replay: queries with a near tie
+    uint16_t* const defer = queue + kFCells;                       // A1 -> A2: queries the 5 x 5 block cannot decide
 
-    if (tid == 0) { s.qn = 0; s.rn = 0; s.dn = 0; s.tn = 0; }
+    if (tid == 0) { s.qn = 0; s.rn = 0; s.dn = 0; s.tn = 0; s.next = 0; }
     if (tid < kFBins) s.hist[tid] = 0;
     if (tid < 5 * 32) {
         const int dy = tid / 32 - 2, w = tid & 31;
@@ -371,20 +374,29 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     __syncthreads();
 
     // ---- pass valid cells through (coalesced), compact masked cells into the queue -------------------------
-#pragma unroll
-    for (int it = 0; it < kFPer; ++it) {
-        const int k = it * kFThreads + tid;
-        const int lj = k / kFW, li = k % kFW;
-        const bool in_range = (J0 + lj < p.row_end) && (I0 + li < W);
-        const int tr = lj + kFHalo, tc = li + kFHalo;
-        const bool valid = (s.mask[tr * 4 + (tc >> 5)] >> (tc & 31)) & 1u;
-        const bool todo = in_range && !valid;
-        if (in_range && valid) __stcs(out_tile + lj * p.out_ld + li, s.tile[tr * kFBW + tc]);
-        const uint32_t m = __ballot_sync(0xffffffffu, todo);
-        int base = 0;
-        if (lane == 0 && m) base = atomicAdd(&s.qn, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (todo) queue[base + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(k);
+    // A warp takes whole tile rows: the row's validity is two words of the bitmask, the same for every lane, so the
+    // queue slots come from popcounts instead of ballots, one shared-memory atomic per row.
+    {
+        const int ncols = min(kFW, W - I0);
+        const uint32_t range_lo = ncols >= 32 ? 0xffffffffu : (1u << ncols) - 1u;
+        const uint32_t range_hi = ncols >= 64 ? 0xffffffffu : (ncols > 32 ? (1u << (ncols - 32)) - 1u : 0u);
+        const uint32_t below = (1u << lane) - 1u;
+        for (int lj = warp; lj < kFH; lj += kFThreads / 32) {
+            if (J0 + lj >= p.row_end) break;
+            const uint32_t* const mrow = s.mask + (lj + kFHalo) * 4;
+            const uint32_t v_lo = __funnelshift_r(mrow[0], mrow[1], kFHalo), v_hi = __funnelshift_r(mrow[1], mrow[2], kFHalo);
+            const uint32_t todo_lo = ~v_lo & range_lo, todo_hi = ~v_hi & range_hi;
+            const int n_lo = __popc(todo_lo), n_row = n_lo + __popc(todo_hi);
+            int base = 0;
+            if (lane == 0 && n_row) base = atomicAdd(&s.qn, n_row);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const T* const trow = s.tile + (lj + kFHalo) * kFBW + kFHalo;
+            T* const orow = out_tile + lj * p.out_ld;
+            if ((v_lo & range_lo) >> lane & 1u) __stcs(orow + lane, trow[lane]);
+            if ((v_hi & range_hi) >> lane & 1u) __stcs(orow + 32 + lane, trow[32 + lane]);
+            if (todo_lo >> lane & 1u) queue[base + __popc(todo_lo & below)] = static_cast<uint16_t>(lj * kFW + lane);
+            if (todo_hi >> lane & 1u) queue[base + n_lo + __popc(todo_hi & below)] = static_cast<uint16_t>(lj * kFW + 32 + lane);
+        }
     }
     __syncthreads();
 
@@ -402,11 +414,15 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     // whose search ends inside the block with at most kFNear candidates takes the near path: its record is the set
     // of candidate cells.  The others are deferred to the general termination scan (phase A2).
     const int qn = s.qn;
-    for (int q = tid; q < qn; q += kFThreads) {
-        const int k = queue[q];
+    for (int qbase = 0; qbase < qn; qbase += kFThreads) {
+        const int q = qbase + tid;
+        const bool live = q < qn;
+        const int k = live ? queue[q] : 0;
         const int lj = k / kFW, li = k % kFW;
         uint32_t rec = 0xffffffffu;                                // "no record"
-        if (isnan(s.x[li]) || isnan(s.y[lj])) {
+        int near_bin = -1;
+        if (!live) {
+        } else if (isnan(s.x[li]) || isnan(s.y[lj])) {
             __stcs(out_tile + lj * p.out_ld + li, static_cast<T>(qnan()));   // query out of bounds
         } else {
             const int ci = s.cx[li] - c0, cj = s.cy[lj] - r0;       // search centre in tile coordinates
@@ -423,15 +439,15 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 const uint32_t cm = n1 >= 4 ? kC1 : (n2 >= 4 ? kC2 : (n3 >= 4 ? kC3 : kC4));
                 const int n = n1 >= 4 ? n1 : (n2 >= 4 ? n2 : (n3 >= 4 ? n3 : n4));
                 if (n >= 4 && n <= kFNear) {
-                    const int bin = kFBinNear + n - 4;
-                    atomicAdd(&s.hist[bin], 1);
-                    rec = (blk & cm) | (static_cast<uint32_t>(bin) << 25);
+                    near_bin = kFBinNear + n - 4;
+                    rec = (blk & cm) | (static_cast<uint32_t>(near_bin) << 25);
                 } else {
                     defer[atomicAdd(&s.dn, 1)] = static_cast<uint16_t>(q);
                 }
             }
         }
-        s.rec[q] = rec; s.reck[q] = static_cast<uint16_t>(k);
+        if (near_bin >= 0) atomicAdd(&s.hist[near_bin], 1);
+        if (live) { s.rec[q] = rec; s.reck[q] = static_cast<uint16_t>(k); }
     }
     __syncthreads();
     // ---- phase A2: general termination scan (rings up to radius 10) for the deferred queries ---------------
@@ -517,34 +533,10 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     __syncthreads();
     const int qb = s.qn, q_near = s.q_near;
 
-    // ---- phase B, near path: one thread per query, candidate list and selection in registers ---------------------
-    // The bins are ordered by candidate count, so a warp's queries have (nearly) the same count: the list length
-    // is a compile-time constant chosen per warp.
-    for (int base = q_near; base < qb; base += kFThreads) {
-        const int q = base + tid;
-        const bool active = q < qb;
-        const uint32_t cand = active ? (s.rec[q] & kC4) : 0u;
-        const int nmax = __reduce_max_sync(0xffffffffu, __popc(cand));
-        if (nmax == 0) continue;
-        const int k = active ? s.reck[q] : 0;
-        if (!active) continue;
-        bool ok;
-        if (nmax <= 4) ok = near_query<T, METHOD, 4, false>(s, p, cand, k, c0, r0, I0, J0, out_tile);
-        else if (nmax <= 6) ok = near_query<T, METHOD, 6, false>(s, p, cand, k, c0, r0, I0, J0, out_tile);
-        else ok = near_query<T, METHOD, kFNear, false>(s, p, cand, k, c0, r0, I0, J0, out_tile);
-        if (!ok) defer[atomicAdd(&s.tn, 1)] = static_cast<uint16_t>(q);
-    }
-    __syncthreads();
-    // ---- phase B, replay of the near-path queries that met a near tie: the same selection on square-rooted distances ---
-    const int tn = s.tn;
-    for (int t = tid; t < tn; t += kFThreads) {
-        const int q = defer[t];
-        near_query<T, METHOD, kFNear, true>(s, p, s.rec[q] & kC4, s.reck[q], c0, r0, I0, J0, out_tile);
-    }
-    __syncthreads();
-
-    // ---- phase B, general path: searches that leave the 5 x 5 block or hold more than kFNear candidates -------------
-    for (int q = tid; q < q_near; q += kFThreads) {
+    // ---- phase B, general path (as a function of the record): searches that leave the 5 x 5 block or hold more than
+    // kFNear candidates.  Candidates in list order into a per-thread list in shared memory, the reference's selection
+    // literally on it (squared distances, with the sqrt guard of each comparison), then the method.
+    auto general_query = [&](int q) {
         const uint32_t rec = s.rec[q];
         const int k = s.reck[q];
         const int r_end = rec & 15, lr_end = (rec >> 4) & 1, n = (rec >> 5) & 31;
@@ -630,7 +622,7 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 lcode[m * kFThreads] = lcode[best * kFThreads]; lcode[best * kFThreads] = cm;
             }
         }
-        if (unsure) { to_literal(k); continue; }
+        if (unsure) { to_literal(k); return; }
         if (cnt >= 4) {
             T v[4];
             double d2v[4];
@@ -654,8 +646,75 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             }
             __stcs(out_tile + lj * p.out_ld + li, finish_few<T, METHOD>(cnt, fv[0], fv[1], fv[2], fd[0], fd[1], fd[2]));
         }
+    };
+
+    // ---- phase B: warps draw chunks of 32 records from a CTA-wide counter ------------------------------------------------
+    // General-path chunks first (they are the long ones), then the near-path chunks; the bins are ordered by candidate
+    // count, so a near chunk's queries have (nearly) the same count and the list length is a compile-time constant
+    // chosen per chunk.  Drawing chunks keeps every warp busy until the records run out whatever the mix.
+    {
+        const int gen_chunks = (q_near + 31) >> 5, all_chunks = gen_chunks + ((qb - q_near + 31) >> 5);
+        for (;;) {
+            int ch = 0;
+            if (lane == 0) ch = atomicAdd(&s.next, 1);
+            ch = __shfl_sync(0xffffffffu, ch, 0);
+            if (ch >= all_chunks) break;
+            if (ch < gen_chunks) {
+                const int q = ch * 32 + lane;
+                if (q < q_near) general_query(q);
+                __syncwarp();
+                continue;
+            }
+            const int q = q_near + (ch - gen_chunks) * 32 + lane;
+            const bool active = q < qb;
+            const uint32_t cand = active ? (s.rec[q] & kC4) : 0u;
+            const int nmax = __reduce_max_sync(0xffffffffu, __popc(cand));
+            if (active) {
+                const int k = s.reck[q];
+                bool ok;
+                if (nmax <= 4) ok = near_query<T, METHOD, 4, false>(s, p, cand, q, k, c0, r0, I0, J0, out_tile);
+                else if (nmax <= 6) ok = near_query<T, METHOD, 6, false>(s, p, cand, q, k, c0, r0, I0, J0, out_tile);
+                else ok = near_query<T, METHOD, kFNear, false>(s, p, cand, q, k, c0, r0, I0, J0, out_tile);
+                if (!ok) {
+                    const int slot = atomicAdd(&s.tn, 1);
+                    if (slot < kFReplayMax) s.replay[slot] = static_cast<uint16_t>(q);
+                    else to_literal(k);
+                }
+            }
+            __syncwarp();
+        }
     }
     __syncthreads();
+    // ---- replay of the near-path queries that met a near tie: the same selection on square-rooted distances ----------
+    const int tn = min(s.tn, kFReplayMax);
+    for (int t = tid; t < tn; t += kFThreads) {
+        const int q = s.replay[t];
+        near_query<T, METHOD, kFNear, true>(s, p, s.rec[q] & kC4, q, s.reck[q], c0, r0, I0, J0, out_tile);
+    }
+    __syncthreads();
+    // ---- kriging of the near-path picks: full warps, nothing else live ------------------------------------------------
+    if (METHOD == KRIGING) {
+        for (int q = q_near + tid; q < qb; q += kFThreads) {
+            const uint32_t rec = s.rec[q];
+            if ((rec >> 25) != 127u) continue;                      // went to the literal path
+            const int k = s.reck[q];
+            const int lj = k / kFW, li = k % kFW;
+            const int cig = s.cx[li], cjg = s.cy[lj];
+            const T* const centre = s.tile + (cjg - r0) * kFBW + (cig - c0);
+            Picked pk;
+            pk.found = 4;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = (rec >> (5 * e)) & 31;
+                const int dxy = s.cell_dxy[c];
+                pk.i[e] = cig + static_cast<int16_t>(dxy & 0xffff); pk.j[e] = cjg + (dxy >> 16);
+                pk.v[e] = static_cast<double>(centre[s.cell_tile[c]]);
+                pk.d[e] = 0.0;
+            }
+            __stcs(out_tile + lj * p.out_ld + li,
+                   static_cast<T>(kriging_from_picked(p.g, pk, __ldg(p.lon.coord + I0 + li), __ldg(p.lat.coord + J0 + lj))));
+        }
+    }
     // ---- queries the bitmask paths handed back: literal per-query evaluation ---------------------------------
     const int rn = min(s.rn, kFRedoMax);
     for (int q = tid; q < rn; q += kFThreads) {
