@@ -29,6 +29,8 @@
 
 using namespace auvi;
 
+namespace auvi { int set_error(const std::string& msg); }   // for the host-only translation units (prep.cpp)
+
 namespace {
 
 thread_local std::string t_error;
@@ -59,24 +61,25 @@ struct AxisOwned {
     }
 };
 
-// Process-wide cache of large device blocks (grid storage, lattice staging).  cudaMalloc/cudaFree of
-// gigabyte blocks cost up to ~150 ms on a busy context (measured: profiles/r01_e2e_pieces.txt); a caller that
-// creates and destroys grids per batch -- as the reference's drivers do -- should not pay that every time.
-// Blocks are only returned here after the device is idle (auvi_grid_destroy synchronises), so reuse on any
-// stream is safe.  At most kCacheBytes are held; auvi_trim() releases them.
+// Process-wide cache of device blocks (grid storage, lattice staging, axis tables).  cudaMalloc/cudaFree cost up
+// to ~150 ms per grid lifetime on a context that also maps a large pinned host buffer -- every cudaFree is a
+// device-wide synchronisation plus page-table work (measured: profiles/r01_e2e_pieces.txt); a caller that creates
+// and destroys grids per batch -- as the reference's drivers do -- should not pay that every time.  Blocks are
+// only returned here after the device is idle (auvi_grid_destroy synchronises), so reuse on any stream is safe.
+// At most kCacheBytes are held; auvi_trim() releases them.
 struct DevBlock { void* p; size_t bytes; int device; };
 std::mutex g_cache_mu;
 std::vector<DevBlock> g_cache;
 size_t g_cache_held = 0;
 constexpr size_t kCacheBytes = 6ull << 30;
-constexpr size_t kCacheMinBlock = 8ull << 20;
+constexpr size_t kCacheMinBlock = 4ull << 10;
 
 cudaError_t cached_malloc(void** out, size_t bytes, int device) {
     if (bytes >= kCacheMinBlock) {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         size_t best = g_cache.size();
         for (size_t k = 0; k < g_cache.size(); ++k)
-            if (g_cache[k].device == device && g_cache[k].bytes >= bytes && g_cache[k].bytes <= bytes + bytes / 4 &&
+            if (g_cache[k].device == device && g_cache[k].bytes >= bytes && g_cache[k].bytes <= bytes + bytes / 4 + 4096 &&
                 (best == g_cache.size() || g_cache[k].bytes < g_cache[best].bytes)) best = k;
         if (best != g_cache.size()) {
             *out = g_cache[best].p;
@@ -118,6 +121,8 @@ constexpr int64_t kLatticeChunkBytes = 256ll << 20; // device staging per pipeli
 
 }  // namespace
 
+int auvi::set_error(const std::string& msg) { return fail(msg); }
+
 struct auvi_grid {
     GridDesc d;
     int device = 0;
@@ -134,8 +139,6 @@ struct auvi_grid {
     void* d_rows[2] = {nullptr, nullptr};
     size_t d_rows_bytes = 0;
     // metrics scratch
-    void* d_scratch = nullptr;
-    double* d_result4 = nullptr;
     std::map<long long, AxisOwned*> axes;             // key: which*2^40 + kind*2^32 + factor
     float last_ms = 0.f;
     int last_tma = 0;
@@ -157,6 +160,13 @@ int check_common(const auvi_grid* g, int method) {
     if (!g) return fail("null grid handle");
     if (method < AUVI_BILINEAR || method > AUVI_IDW) return fail("unknown interpolation method");
     return 0;
+}
+
+void free_axis(AxisOwned* a, int device) {
+    cached_free(a->d_coord, sizeof(double) * a->coord.size(), device);
+    cached_free(a->d_pos, sizeof(double) * a->pos.size(), device);
+    cached_free(a->d_base, sizeof(int) * a->base.size(), device);
+    delete a;
 }
 
 // Per-axis lattice tables.  `which` 0 = longitude (columns), 1 = latitude (rows).
@@ -188,14 +198,13 @@ int get_axis(auvi_grid* g, int which, int kind, int factor, AxisOwned** out) {
         a->base[k] = b < 0 ? 0 : (b > n - 1 ? n - 1 : b);
     }
     cudaError_t e;
-    if ((e = cudaMalloc(&a->d_coord, sizeof(double) * n_out)) != cudaSuccess ||
-        (e = cudaMalloc(&a->d_pos, sizeof(double) * n_out)) != cudaSuccess ||
-        (e = cudaMalloc(&a->d_base, sizeof(int) * n_out)) != cudaSuccess ||
+    if ((e = cached_malloc(reinterpret_cast<void**>(&a->d_coord), sizeof(double) * n_out, g->device)) != cudaSuccess ||
+        (e = cached_malloc(reinterpret_cast<void**>(&a->d_pos), sizeof(double) * n_out, g->device)) != cudaSuccess ||
+        (e = cached_malloc(reinterpret_cast<void**>(&a->d_base), sizeof(int) * n_out, g->device)) != cudaSuccess ||
         (e = cudaMemcpy(a->d_coord, a->coord.data(), sizeof(double) * n_out, cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMemcpy(a->d_pos, a->pos.data(), sizeof(double) * n_out, cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMemcpy(a->d_base, a->base.data(), sizeof(int) * n_out, cudaMemcpyHostToDevice)) != cudaSuccess) {
-        cudaFree(a->d_coord); cudaFree(a->d_pos); cudaFree(a->d_base);
-        delete a;
+        free_axis(a, g->device);
         return fail_cuda("axis table upload", e);
     }
     g->axes[key] = a;
@@ -215,6 +224,28 @@ int fill_desc(GridDesc& d, int dtype, int64_t n_lat, int64_t n_lon, double min_l
     d.lat_step = (max_lat - min_lat) / (d.n_lat - 1);
     return 0;
 }
+
+// Device scratch of one metrics call: the partial sums and the five results, one cached block.
+struct MetricsScratch {
+    void* scratch = nullptr;
+    double* result5 = nullptr;
+    size_t bytes = 0;
+    int device = 0;
+    int open() {
+        AUVI_CUDA(cudaGetDevice(&device));
+        bytes = (metrics_scratch_bytes() + 255) / 256 * 256 + 4096;
+        AUVI_CUDA(cached_malloc(&scratch, bytes, device));
+        result5 = reinterpret_cast<double*>(static_cast<char*>(scratch) + bytes - 4096);
+        return 0;
+    }
+    int close(cudaError_t e, cudaStream_t st, double (&h)[5]) {    // copies the results out and returns the block
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h, result5, sizeof h, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) { cached_free(scratch, bytes, device); return 0; }
+        cudaFree(scratch);
+        return fail_cuda("metrics", e);
+    }
+};
 
 int ensure_point_staging(auvi_grid* g) {
     if (g->h_in[0]) return 0;
@@ -303,10 +334,7 @@ int auvi_grid_destroy(auvi_grid* g) {
     if (!g) return 0;
     cudaSetDevice(g->device);
     cudaDeviceSynchronize();
-    for (auto& kv : g->axes) {
-        cudaFree(kv.second->d_coord); cudaFree(kv.second->d_pos); cudaFree(kv.second->d_base);
-        delete kv.second;
-    }
+    for (auto& kv : g->axes) free_axis(kv.second, g->device);
     for (int k = 0; k < 2; ++k) {
         if (g->h_in[k]) cudaFreeHost(g->h_in[k]);
         if (g->h_out[k]) cudaFreeHost(g->h_out[k]);
@@ -317,7 +345,6 @@ int auvi_grid_destroy(auvi_grid* g) {
         if (g->ev_done[k]) cudaEventDestroy(g->ev_done[k]);
         if (g->st[k]) cudaStreamDestroy(g->st[k]);
     }
-    cudaFree(g->d_scratch); cudaFree(g->d_result4);
     cached_free(g->owned, g->owned_bytes, g->device);
     delete g;
     return 0;
@@ -497,24 +524,142 @@ int auvi_error_metrics_device(const void* dev_truth, const void* dev_est, int dt
     if (n <= 0) return fail("Error: Reference or interpolated points vector is empty or sizes do not match.");
     if (!dev_truth || !dev_est || !out3) return fail("null buffer");
     if (auvi_device_count() <= 0) return fail("no CUDA device: libauvi has no CPU fallback");
-    void* scratch = nullptr;
-    double* result4 = nullptr;
-    AUVI_CUDA(cudaMalloc(&scratch, metrics_scratch_bytes()));
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&result4), sizeof(double) * 4);
-    if (e != cudaSuccess) { cudaFree(scratch); return fail_cuda("cudaMalloc", e); }
+    MetricsScratch ms;
+    if (ms.open()) return 2;
     LaunchInfo info;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    e = launch_metrics(dev_truth, dev_est, dtype, n, scratch, result4, st, &info);
-    double h[4] = {0, 0, 0, 0};
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h, result4, sizeof h, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(scratch); cudaFree(result4);
-    if (e != cudaSuccess) return fail_cuda("metrics", e);
+    cudaError_t e = launch_metrics(dev_truth, dev_est, dtype, n, ms.scratch, ms.result5, st, &info);
+    double h[5];
+    if (ms.close(e, st, h)) return 2;
     g_launches.fetch_add(info.launches);
     out3[0] = h[0] / static_cast<double>(n);                       // error_calculator.cpp:17
     out3[1] = std::sqrt(h[1] / static_cast<double>(n));            // :32
     out3[2] = h[2];
     if (out_nan) *out_nan = static_cast<int64_t>(h[3]);
+    return 0;
+}
+
+int auvi_fill_metrics_device(auvi_grid* masked, const void* dev_filled, int64_t filled_ld, const void* dev_truth,
+                             int64_t truth_ld, int64_t row_begin, int64_t row_end, double* out3, int64_t* out_nan,
+                             int64_t* out_count, void* stream) {
+    if (!masked) return fail("null grid handle");
+    if (!dev_filled || !dev_truth || !out3) return fail("null buffer");
+    const GridDesc& d = masked->d;
+    if (row_begin < d.row0 || row_end > d.row0 + d.rows || row_begin >= row_end) return fail("row range outside the resident slab");
+    if (filled_ld < d.n_lon || truth_ld < d.n_lon) return fail("row pitch must be >= n_lon");
+    AUVI_CUDA(cudaSetDevice(masked->device));
+    MetricsScratch ms;
+    if (ms.open()) return 2;
+    LaunchInfo info;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t es = d.dtype == AUVI_F64 ? 8 : 4;
+    const char* m0 = static_cast<const char*>(d.z) + static_cast<size_t>(row_begin - d.row0) * d.ld * es;
+    cudaError_t e = launch_metrics_masked(m0, d.ld, dev_filled, filled_ld, dev_truth, truth_ld, d.dtype, row_end - row_begin,
+                                          d.n_lon, ms.scratch, ms.result5, st, &info);
+    double h[5];
+    if (ms.close(e, st, h)) return 2;
+    g_launches.fetch_add(info.launches);
+    const double n = h[4];
+    if (out_count) *out_count = static_cast<int64_t>(n);
+    if (out_nan) *out_nan = static_cast<int64_t>(h[3]);
+    if (n <= 0.0) return fail("Error: Reference or interpolated points vector is empty or sizes do not match.");
+    out3[0] = h[0] / n; out3[1] = std::sqrt(h[1] / n); out3[2] = h[2];
+    return 0;
+}
+
+// ---- Grid-B data preparation -------------------------------------------------
+
+int auvi_grid_create_raw(const void* host_raw, int nc_type, int big_endian, int flip_rows, double scale, double offset,
+                         int dtype, int64_t n_lat, int64_t n_lon, double min_lon, double max_lon, double min_lat,
+                         double max_lat, int device, auvi_grid** out) {
+    if (!out) return fail("null output handle");
+    *out = nullptr;
+    if (!host_raw) return fail("null host buffer");
+    if (nc_type < 3 || nc_type > 6) return fail("raw element type must be NC_SHORT(3), NC_INT(4), NC_FLOAT(5) or NC_DOUBLE(6)");
+    if (auvi_device_count() <= 0) return fail("no CUDA device: libauvi has no CPU fallback");
+    auvi_grid* g = new (std::nothrow) auvi_grid;
+    if (!g) return fail("out of host memory");
+    if (fill_desc(g->d, dtype, n_lat, n_lon, min_lon, max_lon, min_lat, max_lat)) { delete g; return 1; }
+    g->device = device;
+    const size_t es = dtype == AUVI_F64 ? 8 : 4, rs = nc_type == 3 ? 2 : (nc_type == 6 ? 8 : 4);
+    const int64_t ld = (n_lon * es + 15) / 16 * 16 / es;
+    const size_t raw_bytes = static_cast<size_t>(n_lat) * n_lon * rs;
+    void* d_raw = nullptr;
+    cudaError_t e = cudaSetDevice(device);
+    g->owned_bytes = static_cast<size_t>(ld) * n_lat * es;
+    if (e == cudaSuccess) e = cached_malloc(&g->owned, g->owned_bytes, device);
+    if (e == cudaSuccess) e = cached_malloc(&d_raw, raw_bytes, device);
+    if (e == cudaSuccess) e = cudaMemcpy(d_raw, host_raw, raw_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_decode_raw(d_raw, nc_type, big_endian, flip_rows, scale, offset, g->d.n_lat, g->d.n_lon,
+                                                g->owned, ld, dtype, nullptr);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (d_raw) cached_free(d_raw, raw_bytes, device);
+    if (e != cudaSuccess) { cudaFree(g->owned); delete g; return fail_cuda("raw grid upload", e); }
+    g_launches.fetch_add(1);
+    g->d.z = g->owned; g->d.ld = ld; g->d.row0 = 0; g->d.rows = g->d.n_lat;
+    if (make_streams(g)) { auvi_grid_destroy(g); return 2; }
+    *out = g;
+    return 0;
+}
+
+int auvi_grid_mask_cells(auvi_grid* g, const int64_t* host_flat_idx, int64_t n, void* host_truth) {
+    if (!g) return fail("null grid handle");
+    if (n < 0) return fail("negative cell count");
+    if (n == 0) return 0;
+    if (!host_flat_idx) return fail("null index list");
+    const int64_t total = static_cast<int64_t>(g->d.n_lat) * g->d.n_lon;
+    for (int64_t k = 0; k < n; ++k)
+        if (host_flat_idx[k] < 0 || host_flat_idx[k] >= total) return fail("cell index outside the grid");
+    AUVI_CUDA(cudaSetDevice(g->device));
+    const size_t es = g->d.dtype == AUVI_F64 ? 8 : 4;
+    void *d_idx = nullptr, *d_truth = nullptr;
+    cudaError_t e = cached_malloc(&d_idx, sizeof(int64_t) * n, g->device);
+    if (e == cudaSuccess && host_truth) e = cached_malloc(&d_truth, es * n, g->device);
+    if (e == cudaSuccess) e = cudaMemcpy(d_idx, host_flat_idx, sizeof(int64_t) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && d_truth) e = cudaMemset(d_truth, 0xff, es * n);          // cells of other slabs stay NaN
+    if (e == cudaSuccess) e = launch_mask_cells(g->d, static_cast<const int64_t*>(d_idx), n, d_truth, nullptr);
+    if (e == cudaSuccess && d_truth) e = cudaMemcpy(host_truth, d_truth, es * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (d_idx) cached_free(d_idx, sizeof(int64_t) * n, g->device);
+    if (d_truth) cached_free(d_truth, es * n, g->device);
+    if (e != cudaSuccess) return fail_cuda("mask cells", e);
+    g_launches.fetch_add(1);
+    return 0;
+}
+
+int auvi_grid_mask_hash(auvi_grid* g, double fraction, uint64_t seed, int64_t* out_masked, void* stream) {
+    if (!g) return fail("null grid handle");
+    if (!(fraction >= 0.0 && fraction <= 1.0)) return fail("mask fraction must lie in [0,1]");
+    AUVI_CUDA(cudaSetDevice(g->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    void* d_cnt = nullptr;
+    if (out_masked) {
+        AUVI_CUDA(cached_malloc(&d_cnt, 4096, g->device));
+        AUVI_CUDA(cudaMemsetAsync(d_cnt, 0, 8, st));
+    }
+    cudaError_t e = launch_mask_hash(g->d, fraction, seed, static_cast<unsigned long long*>(d_cnt), st);
+    if (e == cudaSuccess && out_masked) {
+        unsigned long long h = 0;
+        e = cudaMemcpyAsync(&h, d_cnt, 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        *out_masked = static_cast<int64_t>(h);
+    }
+    if (d_cnt) cached_free(d_cnt, 4096, g->device);
+    if (e != cudaSuccess) return fail_cuda("mask hash", e);
+    g_launches.fetch_add(1);
+    return 0;
+}
+
+int auvi_grid_read(auvi_grid* g, int64_t row_begin, int64_t row_end, void* host_out) {
+    if (!g) return fail("null grid handle");
+    if (row_begin < g->d.row0 || row_end > g->d.row0 + g->d.rows || row_begin > row_end) return fail("row range outside the resident slab");
+    if (row_begin == row_end) return 0;
+    if (!host_out) return fail("null host buffer");
+    AUVI_CUDA(cudaSetDevice(g->device));
+    const size_t es = g->d.dtype == AUVI_F64 ? 8 : 4;
+    AUVI_CUDA(cudaMemcpy2D(host_out, g->d.n_lon * es,
+                           static_cast<const char*>(g->d.z) + static_cast<size_t>(row_begin - g->d.row0) * g->d.ld * es,
+                           g->d.ld * es, g->d.n_lon * es, row_end - row_begin, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -68,10 +68,20 @@ cudaError_t launch_fill(const GridDesc& d, int method, const AxisTables& lat, co
                         int64_t row_end, void* out, int64_t out_ld, cudaStream_t st, LaunchInfo* info);
 
 // metrics.cu -- MAE / RMSE / Max / NaN count of est against truth (error_calculator.cpp:5-45).
-// scratch: device buffer of metrics_scratch_bytes(); result4 (device): {sum|d|, sum d^2, max|d|, #NaN}.
+// scratch: device buffer of metrics_scratch_bytes(); result5 (device): {sum|d|, sum d^2, max|d|, #NaN, #compared}.
 size_t metrics_scratch_bytes();
 cudaError_t launch_metrics(const void* truth, const void* est, int dtype, int64_t n, void* scratch,
-                           double* result4, cudaStream_t st, LaunchInfo* info);
+                           double* result5, cudaStream_t st, LaunchInfo* info);
+// The same over the cells that are NaN in `masked` (the cells a gap fill produced), 2-D with row pitches.
+cudaError_t launch_metrics_masked(const void* masked, int64_t ld_m, const void* filled, int64_t ld_f, const void* truth,
+                                  int64_t ld_t, int dtype, int64_t rows, int cols, void* scratch, double* result5,
+                                  cudaStream_t st, LaunchInfo* info);
+
+// ingest.cu -- Grid-B data preparation on the device (decode a NetCDF variable, mask cells).
+cudaError_t launch_decode_raw(const void* raw, int nc_type, int big_endian, int flip_rows, double scale, double offset,
+                              int n_lat, int n_lon, void* out, int64_t ld, int dtype, cudaStream_t st);
+cudaError_t launch_mask_cells(const GridDesc& d, const int64_t* idx, int64_t n, void* truth, cudaStream_t st);
+cudaError_t launch_mask_hash(const GridDesc& d, double fraction, uint64_t seed, unsigned long long* n_masked, cudaStream_t st);
 
 // Encodes a 2-D tiled tensor map over the grid slab; returns false when TMA cannot address it.
 bool make_grid_tensor_map(const GridDesc& d, int box_w, int box_h, CUtensorMap* out);

@@ -12,10 +12,11 @@ namespace auvi {
 constexpr int kMetBlock = 256;
 constexpr int kMetBlocks = 148 * 8;
 
-struct Partial { double sum_abs, sum_sq, max_abs, n_nan; };
+struct Partial { double sum_abs, sum_sq, max_abs, n_nan, cnt; };
 
 __device__ __forceinline__ void combine(Partial& a, const Partial& b) {
     a.sum_abs += b.sum_abs; a.sum_sq += b.sum_sq; a.max_abs = fmax(a.max_abs, b.max_abs); a.n_nan += b.n_nan;
+    a.cnt += b.cnt;
 }
 
 __device__ __forceinline__ Partial block_reduce(Partial v) {
@@ -27,12 +28,13 @@ __device__ __forceinline__ Partial block_reduce(Partial v) {
         w.sum_sq = __shfl_down_sync(0xffffffffu, v.sum_sq, o);
         w.max_abs = __shfl_down_sync(0xffffffffu, v.max_abs, o);
         w.n_nan = __shfl_down_sync(0xffffffffu, v.n_nan, o);
+        w.cnt = __shfl_down_sync(0xffffffffu, v.cnt, o);
         combine(v, w);
     }
     if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
     __syncthreads();
     if (threadIdx.x < 32) {
-        Partial z{0.0, 0.0, 0.0, 0.0};
+        Partial z{0.0, 0.0, 0.0, 0.0, 0.0};
         v = threadIdx.x < kMetBlock / 32 ? s[threadIdx.x] : z;
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) {
@@ -41,6 +43,7 @@ __device__ __forceinline__ Partial block_reduce(Partial v) {
             w.sum_sq = __shfl_down_sync(0xffffffffu, v.sum_sq, o);
             w.max_abs = __shfl_down_sync(0xffffffffu, v.max_abs, o);
             w.n_nan = __shfl_down_sync(0xffffffffu, v.n_nan, o);
+        w.cnt = __shfl_down_sync(0xffffffffu, v.cnt, o);
             combine(v, w);
         }
     }
@@ -50,7 +53,7 @@ __device__ __forceinline__ Partial block_reduce(Partial v) {
 template <typename T>
 __global__ void __launch_bounds__(kMetBlock)
 metrics_partial_kernel(const T* __restrict__ truth, const T* __restrict__ est, int64_t n, Partial* __restrict__ part) {
-    Partial acc{0.0, 0.0, 0.0, 0.0};
+    Partial acc{0.0, 0.0, 0.0, 0.0, 0.0};
     for (int64_t k = static_cast<int64_t>(blockIdx.x) * kMetBlock + threadIdx.x; k < n;
          k += static_cast<int64_t>(gridDim.x) * kMetBlock) {
         const double t = static_cast<double>(__ldcs(truth + k)), e = static_cast<double>(__ldcs(est + k));
@@ -58,18 +61,44 @@ metrics_partial_kernel(const T* __restrict__ truth, const T* __restrict__ est, i
         if (isnan(e)) acc.n_nan += 1.0;
         else { acc.sum_abs += d; acc.sum_sq += d * d; }
         if (d > acc.max_abs) acc.max_abs = d;                  // false for NaN, like the reference
+        acc.cnt += 1.0;
+    }
+    acc = block_reduce(acc);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+// The same sums over the cells a gap fill produced: cell (r,c) counts iff the MASKED grid holds NaN there, the
+// estimate is the filled grid's cell and the truth the unmasked grid's -- the RMSE of test_gebco.cpp:150-230 without
+// gathering the removed cells into point lists.  3 x sizeof(T) bytes per cell.
+template <typename T>
+__global__ void __launch_bounds__(kMetBlock)
+metrics_masked_partial_kernel(const T* __restrict__ masked, int64_t ld_m, const T* __restrict__ filled, int64_t ld_f,
+                              const T* __restrict__ truth, int64_t ld_t, int64_t rows, int cols, Partial* __restrict__ part) {
+    Partial acc{0.0, 0.0, 0.0, 0.0, 0.0};
+    const int64_t n = rows * cols;
+    for (int64_t k = static_cast<int64_t>(blockIdx.x) * kMetBlock + threadIdx.x; k < n;
+         k += static_cast<int64_t>(gridDim.x) * kMetBlock) {
+        const int64_t r = k / cols;
+        const int c = static_cast<int>(k - r * cols);
+        if (!isnan(__ldcs(masked + r * ld_m + c))) continue;
+        const double t = static_cast<double>(__ldcs(truth + r * ld_t + c)), e = static_cast<double>(__ldcs(filled + r * ld_f + c));
+        const double d = fabs(t - e);
+        if (isnan(e)) acc.n_nan += 1.0;
+        else { acc.sum_abs += d; acc.sum_sq += d * d; }
+        if (d > acc.max_abs) acc.max_abs = d;
+        acc.cnt += 1.0;
     }
     acc = block_reduce(acc);
     if (threadIdx.x == 0) part[blockIdx.x] = acc;
 }
 
 __global__ void __launch_bounds__(kMetBlock)
-metrics_final_kernel(const Partial* __restrict__ part, int n_part, double* __restrict__ result4) {
-    Partial acc{0.0, 0.0, 0.0, 0.0};
+metrics_final_kernel(const Partial* __restrict__ part, int n_part, double* __restrict__ result5) {
+    Partial acc{0.0, 0.0, 0.0, 0.0, 0.0};
     for (int k = threadIdx.x; k < n_part; k += kMetBlock) combine(acc, part[k]);
     acc = block_reduce(acc);
     if (threadIdx.x == 0) {
-        result4[0] = acc.sum_abs; result4[1] = acc.sum_sq; result4[2] = acc.max_abs; result4[3] = acc.n_nan;
+        result5[0] = acc.sum_abs; result5[1] = acc.sum_sq; result5[2] = acc.max_abs; result5[3] = acc.n_nan; result5[4] = acc.cnt;
     }
 }
 
@@ -87,6 +116,25 @@ cudaError_t launch_metrics(const void* truth, const void* est, int dtype, int64_
         metrics_partial_kernel<float><<<blocks, kMetBlock, 0, st>>>(static_cast<const float*>(truth),
                                                                     static_cast<const float*>(est), n, part);
     metrics_final_kernel<<<1, kMetBlock, 0, st>>>(part, blocks, result4);
+    if (info) info->launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_metrics_masked(const void* masked, int64_t ld_m, const void* filled, int64_t ld_f, const void* truth,
+                                  int64_t ld_t, int dtype, int64_t rows, int cols, void* scratch, double* result5,
+                                  cudaStream_t st, LaunchInfo* info) {
+    int64_t want = (rows * cols + kMetBlock - 1) / kMetBlock;
+    const int blocks = static_cast<int>(want < 1 ? 1 : (want > kMetBlocks ? kMetBlocks : want));
+    Partial* part = static_cast<Partial*>(scratch);
+    if (dtype == DT_F64)
+        metrics_masked_partial_kernel<double><<<blocks, kMetBlock, 0, st>>>(
+            static_cast<const double*>(masked), ld_m, static_cast<const double*>(filled), ld_f,
+            static_cast<const double*>(truth), ld_t, rows, cols, part);
+    else
+        metrics_masked_partial_kernel<float><<<blocks, kMetBlock, 0, st>>>(
+            static_cast<const float*>(masked), ld_m, static_cast<const float*>(filled), ld_f,
+            static_cast<const float*>(truth), ld_t, rows, cols, part);
+    metrics_final_kernel<<<1, kMetBlock, 0, st>>>(part, blocks, result5);
     if (info) info->launches += 2;
     return cudaGetLastError();
 }

@@ -39,6 +39,16 @@ SYMBOLS = {
     "auvi_lattice_device": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _i64, _vp, _vp]),
     "auvi_lattice": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _vp]),
     "auvi_error_metrics_device": (_i32, [_vp, _vp, _i32, _i64, C.POINTER(_dbl), C.POINTER(_i64), _vp]),
+    "auvi_fill_metrics_device": (_i32, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, C.POINTER(_dbl), C.POINTER(_i64),
+                                        C.POINTER(_i64), _vp]),
+    "auvi_netcdf3_find": (_i32, [_vp, _i64, C.c_char_p, _vp]),
+    "auvi_netcdf3_read_f64": (_i32, [_vp, _i64, C.c_char_p, _vp, _i64]),
+    "auvi_legacy_choice": (_i32, [_i64, _i64, C.c_uint32, _vp]),
+    "auvi_grid_create_raw": (_i32, [_vp, _i32, _i32, _i32, _dbl, _dbl, _i32, _i64, _i64, _dbl, _dbl, _dbl, _dbl, _i32,
+                                    C.POINTER(_vp)]),
+    "auvi_grid_mask_cells": (_i32, [_vp, _vp, _i64, _vp]),
+    "auvi_grid_mask_hash": (_i32, [_vp, _dbl, C.c_uint64, C.POINTER(_i64), _vp]),
+    "auvi_grid_read": (_i32, [_vp, _i64, _i64, _vp]),
     "auvi_last_error": (C.c_char_p, []),
     "auvi_last_kernel_ms": (C.c_float, [_vp]),
     "auvi_launch_count": (_i64, []),
@@ -88,8 +98,78 @@ def _np_dtype(dtype):
     return np.float64 if dtype == F64 else np.float32
 
 
+class NcVar(C.Structure):
+    """struct auvi_nc_var (include/auvi.h)."""
+    _fields_ = [("nc_type", C.c_int32), ("elem_bytes", C.c_int32), ("ndims", C.c_int32), ("has_fill", C.c_int32),
+                ("shape", C.c_int64 * 4), ("n_elems", C.c_int64), ("data_offset", C.c_int64),
+                ("scale_factor", C.c_double), ("add_offset", C.c_double), ("fill_value", C.c_double)]
+
+
+def netcdf3_find(image: bytes, name: str) -> NcVar:
+    v = NcVar()
+    _check(load().auvi_netcdf3_find(image, len(image), name.encode(), C.byref(v)))
+    return v
+
+
+def netcdf3_read_f64(image: bytes, name: str) -> np.ndarray:
+    v = netcdf3_find(image, name)
+    out = np.empty(v.n_elems, dtype=np.float64)
+    _check(load().auvi_netcdf3_read_f64(image, len(image), name.encode(), out.ctypes.data, out.size))
+    return out.reshape([v.shape[k] for k in range(v.ndims)])
+
+
+def legacy_choice(total: int, n: int, seed: int = 42) -> np.ndarray:
+    """numpy.random.seed(seed); numpy.random.choice(total, n, replace=False) -- restated in C++ (prep.cpp)."""
+    out = np.empty(n, dtype=np.int64)
+    _check(load().auvi_legacy_choice(total, n, seed, out.ctypes.data))
+    return out
+
+
 class Grid:
     """A depth grid resident on one GPU (handle owner)."""
+
+    @classmethod
+    def from_netcdf(cls, image: bytes, var: str, bounds, dtype=F64, flip_rows=True, device=0):
+        """A NetCDF-3 file image -> device grid: the variable's big-endian elements are uploaded as they lie in the
+        file and decoded on the GPU (subset_bathymetry.py:8-18 without netCDF4 / pandas)."""
+        v = netcdf3_find(image, var)
+        assert v.ndims == 2, "a 2-D variable is expected"
+        self = cls.__new__(cls)
+        self._h = _vp()
+        self.bounds = tuple(bounds)
+        self.dtype = dtype
+        self.n_lat, self.n_lon = int(v.shape[0]), int(v.shape[1])
+        raw = (C.c_char * (v.n_elems * v.elem_bytes)).from_buffer_copy(image, v.data_offset)
+        _check(load().auvi_grid_create_raw(raw, v.nc_type, 1, int(flip_rows), v.scale_factor, v.add_offset, dtype,
+                                           self.n_lat, self.n_lon, *bounds, device, C.byref(self._h)))
+        return self
+
+    def mask_cells(self, flat_idx, want_truth=True):
+        """Set the listed cells (row*n_lon+col) to NaN on the device; -> their former values in list order."""
+        flat_idx = np.ascontiguousarray(flat_idx, dtype=np.int64)
+        truth = np.empty(flat_idx.size, dtype=_np_dtype(self.dtype)) if want_truth else None
+        _check(load().auvi_grid_mask_cells(self._h, flat_idx.ctypes.data, flat_idx.size,
+                                           truth.ctypes.data if want_truth else None))
+        return truth
+
+    def mask_hash(self, fraction, seed=42, count=True, stream=None):
+        n = _i64()
+        _check(load().auvi_grid_mask_hash(self._h, fraction, seed, C.byref(n) if count else None, stream))
+        return n.value if count else None
+
+    def read(self, row_begin=0, row_end=None):
+        row_end = self.n_lat if row_end is None else row_end
+        out = np.empty((row_end - row_begin, self.n_lon), dtype=_np_dtype(self.dtype))
+        _check(load().auvi_grid_read(self._h, row_begin, row_end, out.ctypes.data))
+        return out
+
+    def fill_metrics_device(self, filled_ptr, filled_ld, truth_ptr, truth_ld, row_begin, row_end, stream=None):
+        """-> (mae, rmse, max, n_nan, n) over the cells that are NaN in this (masked) grid."""
+        out3 = (_dbl * 3)()
+        nn, cnt = _i64(), _i64()
+        _check(load().auvi_fill_metrics_device(self._h, filled_ptr, filled_ld, truth_ptr, truth_ld, row_begin, row_end,
+                                               out3, C.byref(nn), C.byref(cnt), stream))
+        return out3[0], out3[1], out3[2], nn.value, cnt.value
 
     def __init__(self, z=None, min_lon=0.0, max_lon=0.0, min_lat=0.0, max_lat=0.0, device=0, dtype=None,
                  adopt=None):

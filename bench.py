@@ -353,6 +353,11 @@ def main():
             extra.update(extra_grid_a_points(torch, auvi, local))
             extra.update(extra_grid_a_lattice(torch, auvi, dev, stream, peak))
 
+    if dist is not None and not args.no_extra:
+        res = extra_gap_fill_sharded(torch, auvi, dist, world, rank, dev, stream, peak)
+        if rank == 0:
+            extra.update(res)
+
     # ---- N > 1: the only collective on the path -- gathering output shards to one consumer (not in `value`) ----
     gather = None
     if dist is not None:
@@ -408,15 +413,9 @@ def extra_gap_fill(torch, auvi, dev, stream, peak):
     for n, methods in ((16384, (("idw", auvi.IDW), ("nn", auvi.NN), ("kriging", auvi.KRIGING),
                                 ("nearest4_mean(cubic fallback)", auvi.CUBIC))), (65536, (("idw", auvi.IDW),))):
         z = synth_grid_device(torch, n, n, 0, n, dev)
-        gen = torch.Generator(device=dev)
-        gen.manual_seed(42)
-        rows_per = 4096                                      # mask in row blocks: torch.rand of 65536^2 would need 17 GB more
-        for r in range(0, n, rows_per):
-            m = torch.rand((min(rows_per, n - r), n), device=dev, generator=gen) < 0.70
-            z[r:r + rows_per][m] = float("nan")
-            del m
         g = auvi.Grid(adopt=dict(ptr=z.data_ptr(), dtype=auvi.F32, n_lat=n, n_lon=n, ld=n, row0=0, rows=n, keep=z),
                       min_lon=100.0, max_lon=110.0, min_lat=-10.0, max_lat=0.0, device=dev.index)
+        g.mask_hash(0.70, seed=42, count=False, stream=stream)   # counter-hash mask drawn on the device (csrc/ingest.cu)
         out = torch.empty((n, n), dtype=torch.float32, device=dev)
         for name, meth in methods:
             fn = lambda: g.lattice_device(meth, auvi.AXIS_NODES, 1, 1, 1, 0, n, out.data_ptr(), n, None, stream)
@@ -435,6 +434,45 @@ def extra_gap_fill(torch, auvi, dev, stream, peak):
         g.close()
         del z, out
         torch.cuda.empty_cache()
+    return res
+
+
+def extra_gap_fill_sharded(torch, auvi, dist, world, rank, dev, stream, peak):
+    """BASELINE configs[4] as it is stated: ONE 65536^2 FP32 grid at 70 % mask, IDW gap fill, output rows sharded over the
+    ranks (strong scaling).  Each rank holds its rows + a halo of the known-point input, draws its part of the one global
+    mask from the counter hash (no communication), fills its rows; the time is the max over ranks between barriers."""
+    import shard
+    n = 65536
+    plan = shard.plan_rows(n, 1, world, rank)
+    lo, hi, in_lo, in_hi = plan.row_lo, plan.row_hi, plan.in_lo, plan.in_hi
+    z = synth_grid_device(torch, n, n, in_lo, in_hi, dev)
+    g = auvi.Grid(adopt=dict(ptr=z.data_ptr(), dtype=auvi.F32, n_lat=n, n_lon=n, ld=n, row0=in_lo, rows=in_hi - in_lo,
+                             keep=z), min_lon=100.0, max_lon=110.0, min_lat=-10.0, max_lat=0.0, device=dev.index)
+    g.mask_hash(0.70, seed=42, count=False, stream=stream)
+    out = torch.empty((hi - lo, n), dtype=torch.float32, device=dev)
+    res = {}
+    for name, meth in (("idw", auvi.IDW), ("nn", auvi.NN)):
+        fn = lambda: g.lattice_device(meth, auvi.AXIS_NODES, 1, 1, 1, lo, hi, out.data_ptr(), n, None, stream)
+        fn()
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 3], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nan_left = torch.tensor([int(torch.isnan(out).sum().item())], device=dev, dtype=torch.int64)
+        dist.all_reduce(nan_left)
+        ms = float(t.item())
+        res[f"gap_fill_70pct_{name}_65536sq_f32_sharded_x{world}"] = {
+            "Mcells_per_s": n * n / (ms * 1e-3) / 1e6, "ms": ms, "scaling": "strong", "rows_per_rank": hi - lo,
+            "halo_rows": shard.HALO, "hbm_frac_per_gpu": 8.0 * (hi - lo) * n / (ms * 1e-3) / 1e9 / peak,
+            "nan_left": int(nan_left.item())}
+    g.close()
+    del z, out
+    torch.cuda.empty_cache()
     return res
 
 

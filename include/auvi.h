@@ -100,6 +100,54 @@ int auvi_lattice(auvi_grid* g, int method, int axis_kind, int f_lat, int f_lon, 
 int auvi_error_metrics_device(const void* dev_truth, const void* dev_est, int dtype, int64_t n,
                               double* out3, int64_t* out_nan, void* stream);
 
+/* The same three numbers for a gap fill, without gathering the removed cells into point lists: cell (r,c) of rows
+ * [row_begin,row_end) counts iff `masked` holds NaN there; estimate = dev_filled[(r-row_begin)*filled_ld + c], truth =
+ * dev_truth[(r-row_begin)*truth_ld + c] (both of the grid's dtype).  This is the RMSE block of test_gebco.cpp:198-230
+ * (SURVEY.md s8(f) N3).  out_count = number of cells compared (the reference's N). */
+int auvi_fill_metrics_device(auvi_grid* masked, const void* dev_filled, int64_t filled_ld, const void* dev_truth,
+                             int64_t truth_ld, int64_t row_begin, int64_t row_end, double* out3, int64_t* out_nan,
+                             int64_t* out_count, void* stream);
+
+/* ---- Grid-B data preparation: replaces the reference's host-side tool chain for this path -- netCDF4 read + row flip
+ *      + seeded removal of cells + CSV round trip (code/subset_bathymetry.py:8-85) and the CSV reader of the driver
+ *      (test_gebco.cpp:19-40) -- SURVEY.md s8(f) N1.  Host-only entries work without a GPU. ------------------------ */
+
+/* A variable of a NetCDF-3 classic (CDF-1) or 64-bit-offset (CDF-2) file held in memory. */
+typedef struct auvi_nc_var {
+    int32_t nc_type;       /* 1 byte, 2 char, 3 short, 4 int, 5 float, 6 double */
+    int32_t elem_bytes;
+    int32_t ndims;
+    int32_t has_fill;
+    int64_t shape[4];
+    int64_t n_elems;
+    int64_t data_offset;   /* bytes from the start of the file image; elements are big-endian, row-major */
+    double scale_factor, add_offset, fill_value;
+} auvi_nc_var;
+
+/* Host only: locate `var_name` (GEBCO: "elevation", "lat", "lon") in the file image. */
+int auvi_netcdf3_find(const void* file_image, int64_t n_bytes, const char* var_name, auvi_nc_var* out);
+/* Host only: decode a whole variable to doubles (coordinate axes; applies scale_factor / add_offset). */
+int auvi_netcdf3_read_f64(const void* file_image, int64_t n_bytes, const char* var_name, double* out, int64_t n_out);
+/* Host only: out_idx[0..n) = numpy.random.seed(seed); numpy.random.choice(total, n, replace=False)
+ * (subset_bathymetry.py:32-39: the legacy MT19937 stream, Fisher-Yates permutation prefix). */
+int auvi_legacy_choice(int64_t total, int64_t n, uint32_t seed, int64_t* out_idx);
+
+/* Upload file-order elements (nc_type 3..6, big- or little-endian) and decode them on the device into a grid of
+ * `dtype`: value*scale+offset, optionally flipping the row order (subset_bathymetry.py:16-17 `iloc[::-1]`).
+ * GEBCO int16 tiles move 2 bytes per cell over PCIe instead of 8. */
+int auvi_grid_create_raw(const void* host_raw, int nc_type, int big_endian, int flip_rows, double scale, double offset,
+                         int dtype, int64_t n_lat, int64_t n_lon, double min_lon, double max_lon, double min_lat,
+                         double max_lat, int device, auvi_grid** out);
+/* Remove cells: host_flat_idx[k] = row*n_lon+col (subset_bathymetry.py:39).  The cells become NaN in the grid's own
+ * storage (also for adopted memory); host_truth (optional, n elements of the grid's dtype) receives their former values
+ * in list order -- the third column of reference_missing.csv (:49-56).  Cells outside a slab are skipped (truth NaN). */
+int auvi_grid_mask_cells(auvi_grid* g, const int64_t* host_flat_idx, int64_t n, void* host_truth);
+/* Remove each cell with probability `fraction`, decided by a hash of (GLOBAL flat index, seed): ranks holding slabs of
+ * one grid draw the same mask without communication (BASELINE config 4).  Asynchronous on stream unless out_masked. */
+int auvi_grid_mask_hash(auvi_grid* g, double fraction, uint64_t seed, int64_t* out_masked, void* stream);
+/* Copy grid rows [row_begin,row_end) back to a dense host array of the grid's dtype. */
+int auvi_grid_read(auvi_grid* g, int64_t row_begin, int64_t row_end, void* host_out);
+
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 const char* auvi_last_error(void);          /* thread-local message of the last failure */
 float auvi_last_kernel_ms(const auvi_grid* g); /* device time of the kernels of the last synchronous call */
