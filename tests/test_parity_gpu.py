@@ -517,3 +517,42 @@ def test_config0_grid_a_full_size(auvi):
         else:
             _close(got, want, atol=TIGHT if meth == ob.KRIGING else ATOL, rtol=0 if meth == ob.KRIGING else RTOL)
     g.close()
+
+
+# ---- the tiled gap-fill kernel against the per-query exact path on whole grids ---------------------------------------
+@pytest.mark.parametrize("dtype_name", ["f32", "f64"])
+@pytest.mark.parametrize("frac", [0.2, 0.5, 0.7, 0.9, 0.97, 0.997])
+def test_fill_tiled_equals_exact_path_on_whole_grids(auvi, torch, frac, dtype_name):
+    """Every path of fill_tiled_kernel (near path, sqrt replay, general path, fewer-than-four, literal hand-backs)
+    against lattice_exact_kernel -- the literal restatement checked against the oracle elsewhere -- on every cell:
+    masks from 20 % (many candidates) to 99.7 % (searches run out of rings).  Also run-to-run determinism."""
+    n_lat, n_lon = 1100, 1300
+    tdt = torch.float32 if dtype_name == "f32" else torch.float64
+    dt = auvi.F32 if dtype_name == "f32" else auvi.F64
+    jj = torch.arange(n_lat, device="cuda", dtype=torch.float64)[:, None]
+    ii = torch.arange(n_lon, device="cuda", dtype=torch.float64)[None, :]
+    z = (-4000.0 + 900.0 * torch.sin(ii * 0.013) * torch.cos(jj * 0.017) + 0.37 * ii - 0.21 * jj).to(tdt).contiguous()
+    g = auvi.Grid(adopt=dict(ptr=z.data_ptr(), dtype=dt, n_lat=n_lat, n_lon=n_lon, ld=n_lon, row0=0, rows=n_lat, keep=z),
+                  min_lon=-30.9967, max_lon=-29.4993, min_lat=-0.5035, max_lat=1.0071)
+    g.mask_hash(frac, seed=7, count=False)
+    st = torch.cuda.current_stream().cuda_stream
+    a = torch.empty((n_lat, n_lon), dtype=tdt, device="cuda")
+    b = torch.empty_like(a)
+    c = torch.empty_like(a)
+    sel = torch.empty((n_lat * n_lon, 9), dtype=torch.int32, device="cuda")
+    for meth in (auvi.NN, auvi.CUBIC, auvi.IDW, auvi.KRIGING):
+        g.lattice_device(meth, auvi.AXIS_NODES, 1, 1, 1, 0, n_lat, a.data_ptr(), n_lon, None, st)
+        g.lattice_device(meth, auvi.AXIS_NODES, 1, 1, 1, 0, n_lat, c.data_ptr(), n_lon, None, st)
+        g.lattice_device(meth, auvi.AXIS_NODES, 1, 1, 1, 0, n_lat, b.data_ptr(), n_lon, sel.data_ptr(), st)   # exact path
+        torch.cuda.synchronize()
+        same_run = (a == c) | (torch.isnan(a) & torch.isnan(c))
+        assert bool(same_run.all()), "tiled fill is not deterministic"
+        assert torch.equal(torch.isnan(a), torch.isnan(b)), auvi.METHOD_NAMES[meth]
+        ok = ~torch.isnan(a)
+        if meth in (auvi.NN, auvi.CUBIC):
+            assert torch.equal(a[ok], b[ok]), auvi.METHOD_NAMES[meth]
+        else:
+            tol = (1e-3 if dtype_name == "f32" or meth == auvi.IDW else 1e-6)
+            err = (a[ok].double() - b[ok].double()).abs() - 1e-5 * b[ok].double().abs() * (meth == auvi.IDW or dtype_name == "f32")
+            assert float(err.max()) <= tol, (auvi.METHOD_NAMES[meth], float(err.max()))
+    g.close()
