@@ -5,8 +5,8 @@
 // that nvcc cannot contract a*b+c into an FMA.  The reference's discrete decisions -- floor/round
 // centre, candidate enumeration order, strict-'<' tie breaks -- are decided by last-bit FP64 noise
 // (SURVEY.md section 0, facts 3-4), so they are only reproducible this way.  Bilinear, bicubic and
-// all neighbour selections come out bit-identical to the CPU reference; kriging differs only through
-// exp() (CUDA's is <=1 ulp, glibc's is correctly rounded), i.e. ~1e-10 m.
+// all neighbour selections come out bit-identical to the CPU reference; kriging -- a tolerance method -- is
+// evaluated with fused multiply-adds and an expm1 form of the variogram: <1e-9 m from the reference.
 //
 // The tiled fast paths (upsample.cu, fill.cu) handle clean stencils in bulk and call into this file
 // for every output whose footprint holds a NaN.
@@ -220,11 +220,40 @@ __device__ __forceinline__ int round_centre(double c, int n) {
     return clampi(static_cast<int>(round(c)), 0, n - 1);
 }
 
-__device__ __forceinline__ double variogram(double h) {           // GridH.cpp:371-376
-    return dadd(1.0, dmul(100.0, dsub(1.0, exp(ddiv(-h, 10.0)))));
+// Variogram of the squared separation: nugget 1 + sill 100 * (1 - exp(-h / range 10)), GridH.cpp:371-376.
+// The reference forms 1 - exp(-t) with t = h/10 ~ 1e-4 for bathymetry grids, i.e. by cancellation; here it is
+// -expm1(-t): for t < 1/16 the Taylor polynomial to degree 11 (truncation < 1e-20 relative), else the library
+// expm1.  Against the reference's own rounding of exp(-t) near 1 this moves gamma by ~1e-14 and the kriging
+// prediction by < 1e-9 m (measured on every Grid-B fixture; tests hold kriging to 1e-6 m).
+__device__ __forceinline__ double variogram_sq(double h2) {
+    const double t = sqrt(h2) * 0.1;
+    double em1;                                                    // expm1(-t)
+    if (t < 0.0625) {
+        double q = -1.0 / 39916800.0;
+        q = fma(q, t, 1.0 / 3628800.0);
+        q = fma(q, t, -1.0 / 362880.0);
+        q = fma(q, t, 1.0 / 40320.0);
+        q = fma(q, t, -1.0 / 5040.0);
+        q = fma(q, t, 1.0 / 720.0);
+        q = fma(q, t, -1.0 / 120.0);
+        q = fma(q, t, 1.0 / 24.0);
+        q = fma(q, t, -1.0 / 6.0);
+        q = fma(q, t, 0.5);
+        q = fma(q, t, -1.0);
+        em1 = q * t;
+    } else {
+        em1 = expm1(-t);
+    }
+    return fma(-100.0, em1, 1.0);
 }
 
 // ---- ordinary kriging on the four picked cells, GridH.cpp:361-419 ----------------------------------
+// Same system as the reference (5 x 5, Lagrange row), solved by Gaussian elimination without pivoting -- the
+// pivots are the reference's Gauss-Jordan pivots, so its singularity test (|pivot| < 1e-12 -> mean of the four)
+// fires on the same systems -- with fused multiply-adds and one reciprocal per pivot, then back substitution:
+// ~65 FP64 operations instead of ~135 + 30 divisions.  Kriging is a tolerance method (the reference's own CPU
+// and GPU paths differ through exp), so operation order is free here; the discrete part -- which four cells --
+// is decided before this function and is bit-exact.
 template <typename T>
 __device__ double kriging_from_picked(const GridView<T>& g, const Picked& p, double lon, double lat) {
     double px[4], py[4];
@@ -233,45 +262,46 @@ __device__ double kriging_from_picked(const GridView<T>& g, const Picked& p, dou
         px[k] = dadd(g.min_lon, dmul(dadd(static_cast<double>(p.i[k]), 0.5), g.lon_step));
         py[k] = dadd(g.min_lat, dmul(dadd(static_cast<double>(p.j[k]), 0.5), g.lat_step));
     }
-    // The variogram matrix is symmetric with gamma(0) = 1 + 100*(1 - exp(-0)) = 1 exactly on the diagonal, so
-    // the six upper-triangle entries are evaluated (same operations as the reference, the squared differences
-    // are sign-symmetric) and mirrored: 10 exp() per query instead of 20.
+    // symmetric variogram matrix with gamma(0) = 1 on the diagonal: six pair entries + four query entries
     double M[5][6];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         M[a][a] = 1.0;
 #pragma unroll
         for (int b = a + 1; b < 4; ++b) {
-            double dx = dsub(px[a], px[b]), dy = dsub(py[a], py[b]);
-            M[a][b] = variogram(dsqrt(dadd(dmul(dx, dx), dmul(dy, dy))));
+            const double dx = px[a] - px[b], dy = py[a] - py[b];
+            M[a][b] = variogram_sq(fma(dx, dx, dy * dy));
             M[b][a] = M[a][b];
         }
         M[a][4] = 1.0; M[4][a] = 1.0;
-        double dx = dsub(px[a], lon), dy = dsub(py[a], lat);        // raw query lon/lat, :380
-        M[a][5] = variogram(dsqrt(dadd(dmul(dx, dx), dmul(dy, dy))));
+        const double dx = px[a] - lon, dy = py[a] - lat;           // raw query lon/lat, :380
+        M[a][5] = variogram_sq(fma(dx, dx, dy * dy));
     }
     M[4][4] = 0.0; M[4][5] = 1.0;
-    // Gauss-Jordan without pivoting (GridH.cpp:401-414).  Only the columns right of the pivot are ever read
-    // again, and the row is scaled by one reciprocal instead of six divisions: differs from the reference's
-    // quotients by <= 1 ulp per element, ~1e-10 m in the prediction (tests hold kriging to 1e-6 m).
+    double inv[5];
 #pragma unroll
     for (int r = 0; r < 5; ++r) {
         const double piv = M[r][r];
-        if (fabs(piv) < 1e-12) return mean_valid4(p.v[0], p.v[1], p.v[2], p.v[3]);
-        const double inv = ddiv(1.0, piv);
+        if (fabs(piv) < 1e-12) return mean_valid4(p.v[0], p.v[1], p.v[2], p.v[3]);   // :403-406
+        inv[r] = 1.0 / piv;
 #pragma unroll
-        for (int q = r + 1; q < 6; ++q) M[r][q] = dmul(M[r][q], inv);
+        for (int k = r + 1; k < 5; ++k) {
+            const double f = M[k][r] * inv[r];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            if (k == r) continue;
-            const double f = M[k][r];
-#pragma unroll
-            for (int q = r + 1; q < 6; ++q) M[k][q] = dsub(M[k][q], dmul(f, M[r][q]));
+            for (int q = r + 1; q < 6; ++q) M[k][q] = fma(-f, M[r][q], M[k][q]);
         }
+    }
+    double w[5];
+#pragma unroll
+    for (int r = 4; r >= 0; --r) {
+        double acc = M[r][5];
+#pragma unroll
+        for (int q = r + 1; q < 5; ++q) acc = fma(-M[r][q], w[q], acc);
+        w[r] = acc * inv[r];
     }
     double out = 0.0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) out = dadd(out, dmul(M[k][5], p.v[k]));
+    for (int k = 0; k < 4; ++k) out = fma(w[k], p.v[k], out);      // :417-418
     return out;
 }
 
