@@ -105,6 +105,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPU cores NVML reports as local to GPU `index`, so that the pinned host buffers
+    the end-to-end leg allocates are first-touched on the GPU's own NUMA node (with one rank per GPU the
+    device->host copies of all ranks otherwise cross the socket link).  Returns the core list or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cores = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1 and 64 * w + b < n_cpu]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return allowed
+    except Exception:
+        pass
+    return None
+
+
 def synth_grid_device(torch, n_lat_global, n_lon, row_lo, row_hi, device):
     """Rows [row_lo,row_hi) of the seamount field (generate_csv_grids.cpp:32-70) in FP32, on device.
     Evaluated in FP64 in 1024-row blocks so that the temporaries stay small next to the 17 GB outputs."""
@@ -194,6 +214,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cores = sorted(os.sched_getaffinity(0))
+    numa = bind_to_gpu_numa_node(local)                              # host buffers of this rank live next to its GPU
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -323,7 +345,8 @@ def main():
         e2e = {"value": e2e_cells / dt / 1e6, "unit": "Mcells/s", "rows_per_rank": e2e_rows, "rows_of_shard": my_rows, "h2d_bytes_per_step": int(h_z.numel() * 4),
                "d2h_bytes_per_step": int(e2e_rows * out_cols * 4), "ms_per_step": dt * 1e3, "steps": e2e_steps,
                "pinned_host": bool(h_out.is_pinned()), "pieces_ms": {k: v / e2e_steps for k, v in pieces.items()},
-               "api": "auvi_grid_create + auvi_lattice(host_out) + auvi_grid_destroy"}
+               "api": "auvi_grid_create + auvi_lattice(host_out) + auvi_grid_destroy",
+               "cpu_affinity": (f"{numa[0]}-{numa[-1]} ({len(numa)} cores, NVML GPU-local)" if numa else "unbound")}
         # raw pinned device->host copy bandwidth of this box, for context (the e2e step moves 16x more bytes D2H than H2D)
         try:
             probe_d = torch.empty(1 << 28, dtype=torch.float32, device=dev)
@@ -384,6 +407,7 @@ def main():
         del recv
 
     cpu = None
+    os.sched_setaffinity(0, all_cores)                               # the CPU baseline gets every core of the box back
     if rank == 0 and not args.no_cpu:
         threads = os.cpu_count() or 1
         rate, kind, cores, ms_cpu, sample = cpu_reference_rate(CPU_SAMPLE_ROWS, threads)
