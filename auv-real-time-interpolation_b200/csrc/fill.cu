@@ -2,8 +2,9 @@
 // cells pass through.  This is the structured form of the reference's Grid-B procedure
 // (test_gebco.cpp:150-196: one query per removed cell, built by gridIndexToGeo :72-81, evaluated by
 // GridH::batch{Cubic,OrdinaryKriging}Interpolate, GridH.cpp:223-420) and of BASELINE config 4
-// (IDW / nearest-neighbour on a 70 % masked grid).  Methods: CUBIC (always the ring-search
-// 4-nearest mean here: a masked cell is inside its own 4x4 stencil), KRIGING, NN, IDW.
+// (IDW / nearest-neighbour on a 70 % masked grid).  Methods: BILINEAR (four corners, NaN-corner mean:
+// no search), CUBIC (always the ring-search 4-nearest mean here: a masked cell is inside its own 4x4
+// stencil), KRIGING, NN, IDW.
 //
 // Design (one CTA = 256 threads = one 64 x 32 tile of cells):
 //   1. The tile + a 12-cell halo (88 x 56 cells: search radius 10 + a centre that FP64 noise may move
@@ -334,7 +335,7 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         int c = 0;
         if (I < W) {
             x = __ldg(p.lon.pos + I);
-            c = METHOD == CUBIC ? __ldg(p.lon.base + I) : (isnan(x) ? 0 : round_centre(x, p.g.n_lon));
+            c = (METHOD == CUBIC || METHOD == BILINEAR) ? __ldg(p.lon.base + I) : (isnan(x) ? 0 : round_centre(x, p.g.n_lon));
         }
         s.x[tid] = x; s.cx[tid] = c;
         const double cf = dadd(__int2double_rn(c), 0.5);
@@ -347,7 +348,7 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         int c = 0;
         if (J < p.row_end) {
             y = __ldg(p.lat.pos + J);
-            c = METHOD == CUBIC ? __ldg(p.lat.base + J) : (isnan(y) ? 0 : round_centre(y, p.g.n_lat));
+            c = (METHOD == CUBIC || METHOD == BILINEAR) ? __ldg(p.lat.base + J) : (isnan(y) ? 0 : round_centre(y, p.g.n_lat));
         }
         s.y[t] = y; s.cy[t] = c;
         const double cf = dadd(__int2double_rn(c), 0.5);
@@ -399,6 +400,35 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         }
     }
     __syncthreads();
+
+    // ---- BILINEAR: no search -- the four corners around the query sit in the tile (GridH.cpp:160-210) -----------------
+    if (METHOD == BILINEAR) {
+        const int qn_b = s.qn;
+        for (int q = tid; q < qn_b; q += kFThreads) {
+            const int k = queue[q];
+            const int lj = k / kFW, li = k % kFW;
+            const double x = s.x[li], y = s.y[lj];
+            double result = qnan();
+            if (!isnan(x) && !isnan(y)) {
+                const int x0 = s.cx[li], y0 = s.cy[lj];             // floor(x), floor(y)
+                const int x1 = min(x0 + 1, p.g.n_lon - 1), y1 = min(y0 + 1, p.g.n_lat - 1);
+                const double wx = dsub(x, __int2double_rn(x0)), wy = dsub(y, __int2double_rn(y0));
+                const T* const r0p = s.tile + (y0 - r0) * kFBW - c0;
+                const T* const r1p = s.tile + (y1 - r0) * kFBW - c0;
+                const double a = static_cast<double>(r0p[x0]), b = static_cast<double>(r0p[x1]);
+                const double c = static_cast<double>(r1p[x0]), d = static_cast<double>(r1p[x1]);
+                if (isnan(a) || isnan(b) || isnan(c) || isnan(d)) result = mean_valid4(a, b, c, d);
+                else {
+                    const double ux = dsub(1.0, wx);
+                    const double lo = dadd(dmul(ux, a), dmul(wx, b));
+                    const double hi = dadd(dmul(ux, c), dmul(wx, d));
+                    result = dadd(dmul(dsub(1.0, wy), lo), dmul(wy, hi));
+                }
+            }
+            __stcs(out_tile + lj * p.out_ld + li, static_cast<T>(result));
+        }
+        return;
+    }
 
     auto window = [&](int row, int wi, int sh) -> uint32_t {       // validity of columns ci-10..ci+10 of a tile row
         return __funnelshift_r(s.mask[row * 4 + wi], s.mask[row * 4 + wi + 1], sh) & 0x1FFFFFu;
@@ -759,9 +789,9 @@ cudaError_t launch_fill(const GridDesc& d, int method, const AxisTables& lat, co
 #define AUVI_CASE(T, M) \
     case M: return launch_fill_t<T, M>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
     if (d.dtype == DT_F64) {
-        switch (method) { AUVI_CASE(double, CUBIC) AUVI_CASE(double, KRIGING) AUVI_CASE(double, NN) AUVI_CASE(double, IDW) }
+        switch (method) { AUVI_CASE(double, BILINEAR) AUVI_CASE(double, CUBIC) AUVI_CASE(double, KRIGING) AUVI_CASE(double, NN) AUVI_CASE(double, IDW) }
     } else {
-        switch (method) { AUVI_CASE(float, CUBIC) AUVI_CASE(float, KRIGING) AUVI_CASE(float, NN) AUVI_CASE(float, IDW) }
+        switch (method) { AUVI_CASE(float, BILINEAR) AUVI_CASE(float, CUBIC) AUVI_CASE(float, KRIGING) AUVI_CASE(float, NN) AUVI_CASE(float, IDW) }
     }
 #undef AUVI_CASE
     return cudaErrorInvalidValue;

@@ -63,7 +63,7 @@ cudaError_t launch_lattice(const GridDesc& d, int method, const AxisTables& lat,
                            int64_t row_begin, int64_t row_end, void* out, int64_t out_ld,
                            int fill, int32_t* sel, cudaStream_t st, LaunchInfo* info);
 
-// fill.cu -- tiled full-grid gap fill (AXIS_NODES, factor 1): CUBIC (ring-search mean), KRIGING, NN, IDW.
+// fill.cu -- tiled full-grid gap fill (AXIS_NODES, factor 1): BILINEAR, CUBIC (ring-search mean), KRIGING, NN, IDW.
 cudaError_t launch_fill(const GridDesc& d, int method, const AxisTables& lat, const AxisTables& lon, int64_t row_begin,
                         int64_t row_end, void* out, int64_t out_ld, cudaStream_t st, LaunchInfo* info);
 

@@ -453,7 +453,7 @@ static cudaError_t launch_lattice_t(const GridDesc& d, int method, const AxisTab
         if (method == BILINEAR) return launch_tiled<T, BILINEAR>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
         if (method == CUBIC) return launch_tiled<T, CUBIC>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
     }
-    if (fill && !sel && method != BILINEAR) {
+    if (fill && !sel) {
         static const bool v0 = getenv("AUVI_FILL_V0") != nullptr;        // A-B measurements only
         if (!v0) return launch_fill(d, method, lat, lon, row_begin, row_end, out, out_ld, st, info);
     }

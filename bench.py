@@ -434,7 +434,7 @@ def extra_gap_fill(torch, auvi, dev, stream, peak):
     """BASELINE configs[4] on one GPU: FP32 grid at 70 % mask, full-grid gap fill -- every method at 16384^2 and
     the IDW headline of that config at the full 65536^2 (17.2 GB in + 17.2 GB out on one B200)."""
     res = {}
-    for n, methods in ((16384, (("idw", auvi.IDW), ("nn", auvi.NN), ("kriging", auvi.KRIGING),
+    for n, methods in ((16384, (("idw", auvi.IDW), ("nn", auvi.NN), ("kriging", auvi.KRIGING), ("bilinear", auvi.BILINEAR),
                                 ("nearest4_mean(cubic fallback)", auvi.CUBIC))), (65536, (("idw", auvi.IDW),))):
         z = synth_grid_device(torch, n, n, 0, n, dev)
         g = auvi.Grid(adopt=dict(ptr=z.data_ptr(), dtype=auvi.F32, n_lat=n, n_lon=n, ld=n, row0=0, rows=n, keep=z),

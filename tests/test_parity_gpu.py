@@ -540,7 +540,7 @@ def test_fill_tiled_equals_exact_path_on_whole_grids(auvi, torch, frac, dtype_na
     b = torch.empty_like(a)
     c = torch.empty_like(a)
     sel = torch.empty((n_lat * n_lon, 9), dtype=torch.int32, device="cuda")
-    for meth in (auvi.NN, auvi.CUBIC, auvi.IDW, auvi.KRIGING):
+    for meth in (auvi.BILINEAR, auvi.NN, auvi.CUBIC, auvi.IDW, auvi.KRIGING):
         g.lattice_device(meth, auvi.AXIS_NODES, 1, 1, 1, 0, n_lat, a.data_ptr(), n_lon, None, st)
         g.lattice_device(meth, auvi.AXIS_NODES, 1, 1, 1, 0, n_lat, c.data_ptr(), n_lon, None, st)
         g.lattice_device(meth, auvi.AXIS_NODES, 1, 1, 1, 0, n_lat, b.data_ptr(), n_lon, sel.data_ptr(), st)   # exact path
@@ -549,7 +549,7 @@ def test_fill_tiled_equals_exact_path_on_whole_grids(auvi, torch, frac, dtype_na
         assert bool(same_run.all()), "tiled fill is not deterministic"
         assert torch.equal(torch.isnan(a), torch.isnan(b)), auvi.METHOD_NAMES[meth]
         ok = ~torch.isnan(a)
-        if meth in (auvi.NN, auvi.CUBIC):
+        if meth in (auvi.BILINEAR, auvi.NN, auvi.CUBIC):
             assert torch.equal(a[ok], b[ok]), auvi.METHOD_NAMES[meth]
         else:
             tol = (1e-3 if dtype_name == "f32" or meth == auvi.IDW else 1e-6)
