@@ -172,6 +172,19 @@ def cpu_reference_rate(sample_rows, threads, steps=1, warmup=0, method=1):
     return pts.shape[0] / dt / 1e6, kind, cores, dt * 1e3, sample
 
 
+def workload_config(world):
+    """The `config` object both arms print: BASELINE configs[3], weak-scaled by rows over `world` GPUs."""
+    import shard
+    out_rows = FACTOR * (N_GRID * world - 1) + 1
+    out_cols = FACTOR * (N_GRID - 1) + 1
+    return {"workload": "BASELINE configs[3]: synthetic 16384x16384 FP32 depth grid, 4x bicubic upsample "
+                        "(per GPU; N GPUs hold a (16384*N) x 16384 grid, output rows sharded)",
+            "grid_per_gpu": [N_GRID, N_GRID], "factor": FACTOR, "method": "bicubic Catmull-Rom",
+            "out_cells_per_gpu": -(-out_rows // world) * out_cols,
+            "parallelism": f"row-sharded x{world}, halo {shard.HALO} rows, no collective",
+            "l2_policy": "inputs (1.07 GB) and outputs (17.2 GB) per step exceed the 126 MB L2"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -181,9 +194,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "Mcells/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[3]: synthetic 16384x16384 depth grid, 4x bicubic upsample",
-                       "grid": [N_GRID, N_GRID], "factor": FACTOR, "method": "bicubic Catmull-Rom",
-                       "step": "bounded sample: " + sample},
+            "config": dict(workload_config(args.gpus), reference_step="bounded sample: " + sample),
             "cpu_baseline": {"value": rate, "unit": "Mcells/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": rate, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -417,11 +428,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "BASELINE configs[3]: synthetic 16384x16384 FP32 depth grid, 4x bicubic upsample "
-                                       "(per GPU; N GPUs hold a (16384*N) x 16384 grid, output rows sharded)",
-                           "grid_per_gpu": [N_GRID, N_GRID], "factor": FACTOR, "method": "bicubic Catmull-Rom",
-                           "out_cells_per_gpu": cells_rank, "parallelism": f"row-sharded x{world}, halo {halo} rows, no collective",
-                           "l2_policy": "inputs (1.07 GB) and outputs (17.2 GB) per step exceed the 126 MB L2"},
+                "config": workload_config(world),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
                 "gather": gather, "extra": extra}
         print(json.dumps(line), flush=True)
