@@ -80,6 +80,8 @@ struct FillParams {
     int rows_resident_lo, rows_resident_hi;   // global rows [lo,hi) present in g.z
     T* out;
     int64_t out_ld;
+    int n_out_cols;                           // lattice columns (== g.n_lon on the node lattice)
+    int f_lat, f_lon;                         // integer upsampling factors of the lattice axes (1 on the node lattice)
     int use_tma;
 };
 
@@ -278,17 +280,19 @@ __device__ __forceinline__ bool near_query(FillSmem<T>& s, const FillParams<T>& 
     return true;
 }
 
-template <typename T, int METHOD>
+template <typename T, int METHOD, bool FILL>
 __global__ void __launch_bounds__(kFThreads, 3)
 fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FillParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FillSmem<T>& s = *reinterpret_cast<FillSmem<T>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int W = p.g.n_lon;
+    const int W = p.g.n_lon;                                       // grid columns; the lattice has p.n_out_cols
     const int I0 = blockIdx.x * kFW;
     const int64_t J0 = p.row_begin + static_cast<int64_t>(blockIdx.y) * kFH;
-    const int c0 = I0 - kFHalo;                                   // 16-byte aligned for f32 and f64
-    const int r0 = static_cast<int>(J0) - kFHalo;
+    // first grid column / row of the staged block: the tile's first node minus the halo, the column rounded down to a
+    // 16-byte boundary for TMA (on the node lattice I0 - 12 already is one)
+    const int c0 = (I0 / p.f_lon - kFHalo) & ~3;
+    const int r0 = static_cast<int>(J0 / p.f_lat) - kFHalo;
     T* const out_tile = p.out + (J0 - p.row_begin) * p.out_ld + I0;
     // two queues live in the general path's list storage until that path starts:
     uint16_t* const queue = reinterpret_cast<uint16_t*>(s.d2);     // masked cells of the tile, compacted (read by phase A1)
@@ -333,7 +337,7 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const int I = I0 + tid;
         double x = qnan();
         int c = 0;
-        if (I < W) {
+        if (I < p.n_out_cols) {
             x = __ldg(p.lon.pos + I);
             c = (METHOD == CUBIC || METHOD == BILINEAR) ? __ldg(p.lon.base + I) : (isnan(x) ? 0 : round_centre(x, p.g.n_lon));
         }
@@ -378,7 +382,7 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     // A warp takes whole tile rows: the row's validity is two words of the bitmask, the same for every lane, so the
     // queue slots come from popcounts instead of ballots, one shared-memory atomic per row.
     {
-        const int ncols = min(kFW, W - I0);
+        const int ncols = min(kFW, p.n_out_cols - I0);
         const uint32_t range_lo = ncols >= 32 ? 0xffffffffu : (1u << ncols) - 1u;
         const uint32_t range_hi = ncols >= 64 ? 0xffffffffu : (ncols > 32 ? (1u << (ncols - 32)) - 1u : 0u);
         const uint32_t below = (1u << lane) - 1u;
@@ -386,15 +390,17 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             if (J0 + lj >= p.row_end) break;
             const uint32_t* const mrow = s.mask + (lj + kFHalo) * 4;
             const uint32_t v_lo = __funnelshift_r(mrow[0], mrow[1], kFHalo), v_hi = __funnelshift_r(mrow[1], mrow[2], kFHalo);
-            const uint32_t todo_lo = ~v_lo & range_lo, todo_hi = ~v_hi & range_hi;
+            const uint32_t todo_lo = FILL ? ~v_lo & range_lo : range_lo, todo_hi = FILL ? ~v_hi & range_hi : range_hi;
             const int n_lo = __popc(todo_lo), n_row = n_lo + __popc(todo_hi);
             int base = 0;
             if (lane == 0 && n_row) base = atomicAdd(&s.qn, n_row);
             base = __shfl_sync(0xffffffffu, base, 0);
             const T* const trow = s.tile + (lj + kFHalo) * kFBW + kFHalo;
             T* const orow = out_tile + lj * p.out_ld;
-            if ((v_lo & range_lo) >> lane & 1u) __stcs(orow + lane, trow[lane]);
-            if ((v_hi & range_hi) >> lane & 1u) __stcs(orow + 32 + lane, trow[32 + lane]);
+            if (FILL) {
+                if ((v_lo & range_lo) >> lane & 1u) __stcs(orow + lane, trow[lane]);
+                if ((v_hi & range_hi) >> lane & 1u) __stcs(orow + 32 + lane, trow[32 + lane]);
+            }
             if (todo_lo >> lane & 1u) queue[base + __popc(todo_lo & below)] = static_cast<uint16_t>(lj * kFW + lane);
             if (todo_hi >> lane & 1u) queue[base + n_lo + __popc(todo_hi & below)] = static_cast<uint16_t>(lj * kFW + 32 + lane);
         }
@@ -754,11 +760,11 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
-template <typename T, int METHOD>
+template <typename T, int METHOD, bool FILL>
 static cudaError_t launch_fill_t(const GridDesc& d, const AxisTables& lat, const AxisTables& lon, int64_t row_begin,
                                  int64_t row_end, void* out, int64_t out_ld, cudaStream_t st, LaunchInfo* info) {
     // rows within the ring-search reach of the block must be resident (slab + halo)
-    int need_lo = static_cast<int>(row_begin) - (kMaxRadius + 2), need_hi = static_cast<int>(row_end) - 1 + (kMaxRadius + 2);
+    int need_lo = lat.h_base[row_begin] - (kMaxRadius + 2), need_hi = lat.h_base[row_end - 1] + 1 + (kMaxRadius + 2);
     need_lo = need_lo < 0 ? 0 : need_lo;
     need_hi = need_hi > d.n_lat - 1 ? d.n_lat - 1 : need_hi;
     if (need_lo < d.row0 || need_hi >= d.row0 + d.rows) return cudaErrorInvalidValue;
@@ -770,28 +776,42 @@ static cudaError_t launch_fill_t(const GridDesc& d, const AxisTables& lat, const
     p.row_begin = row_begin; p.row_end = row_end;
     p.rows_resident_lo = d.row0; p.rows_resident_hi = d.row0 + d.rows;
     p.out = static_cast<T*>(out); p.out_ld = out_ld;
+    p.n_out_cols = lon.n;
+    p.f_lat = d.n_lat > 1 ? (lat.n - 1) / (d.n_lat - 1) : 1;
+    p.f_lon = d.n_lon > 1 ? (lon.n - 1) / (d.n_lon - 1) : 1;
+    if (p.f_lat < 1 || p.f_lon < 1 || (FILL && (p.f_lat != 1 || p.f_lon != 1))) return cudaErrorInvalidValue;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
     p.use_tma = make_grid_tensor_map(d, kFBW, kFBH, &tmap) ? 1 : 0;
-    auto kern = fill_tiled_kernel<T, METHOD>;
+    auto kern = fill_tiled_kernel<T, METHOD, FILL>;
     const size_t smem = sizeof(FillSmem<T>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    dim3 grid(static_cast<unsigned>((d.n_lon + kFW - 1) / kFW), static_cast<unsigned>((row_end - row_begin + kFH - 1) / kFH));
+    dim3 grid(static_cast<unsigned>((lon.n + kFW - 1) / kFW), static_cast<unsigned>((row_end - row_begin + kFH - 1) / kFH));
     kern<<<grid, kFThreads, smem, st>>>(tmap, p);
     if (info) { info->launches += 1; info->used_tma = p.use_tma; }
     return cudaGetLastError();
 }
 
 cudaError_t launch_fill(const GridDesc& d, int method, const AxisTables& lat, const AxisTables& lon, int64_t row_begin,
-                        int64_t row_end, void* out, int64_t out_ld, cudaStream_t st, LaunchInfo* info) {
+                        int64_t row_end, void* out, int64_t out_ld, int fill, cudaStream_t st, LaunchInfo* info) {
     if (row_end <= row_begin) return cudaSuccess;
-#define AUVI_CASE(T, M) \
-    case M: return launch_fill_t<T, M>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
-    if (d.dtype == DT_F64) {
-        switch (method) { AUVI_CASE(double, BILINEAR) AUVI_CASE(double, CUBIC) AUVI_CASE(double, KRIGING) AUVI_CASE(double, NN) AUVI_CASE(double, IDW) }
-    } else {
-        switch (method) { AUVI_CASE(float, BILINEAR) AUVI_CASE(float, CUBIC) AUVI_CASE(float, KRIGING) AUVI_CASE(float, NN) AUVI_CASE(float, IDW) }
+#define AUVI_CASE(T, M, F) \
+    case M: return launch_fill_t<T, M, F>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
+    if (fill) {
+        if (d.dtype == DT_F64) {
+            switch (method) { AUVI_CASE(double, BILINEAR, true) AUVI_CASE(double, CUBIC, true) AUVI_CASE(double, KRIGING, true)
+                              AUVI_CASE(double, NN, true) AUVI_CASE(double, IDW, true) }
+        } else {
+            switch (method) { AUVI_CASE(float, BILINEAR, true) AUVI_CASE(float, CUBIC, true) AUVI_CASE(float, KRIGING, true)
+                              AUVI_CASE(float, NN, true) AUVI_CASE(float, IDW, true) }
+        }
+    } else {                                   // upsampling lattice, the search-based methods (every cell is a query)
+        if (d.dtype == DT_F64) {
+            switch (method) { AUVI_CASE(double, KRIGING, false) AUVI_CASE(double, NN, false) AUVI_CASE(double, IDW, false) }
+        } else {
+            switch (method) { AUVI_CASE(float, KRIGING, false) AUVI_CASE(float, NN, false) AUVI_CASE(float, IDW, false) }
+        }
     }
 #undef AUVI_CASE
     return cudaErrorInvalidValue;

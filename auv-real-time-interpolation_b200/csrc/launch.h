@@ -63,9 +63,11 @@ cudaError_t launch_lattice(const GridDesc& d, int method, const AxisTables& lat,
                            int64_t row_begin, int64_t row_end, void* out, int64_t out_ld,
                            int fill, int32_t* sel, cudaStream_t st, LaunchInfo* info);
 
-// fill.cu -- tiled full-grid gap fill (AXIS_NODES, factor 1): BILINEAR, CUBIC (ring-search mean), KRIGING, NN, IDW.
+// fill.cu -- the tiled ring-search kernel.  fill != 0: full-grid gap fill on the node lattice (AXIS_NODES, factor 1),
+// BILINEAR, CUBIC (ring-search mean), KRIGING, NN, IDW.  fill == 0: KRIGING / NN / IDW on an upsampling lattice
+// (integer factors), every output cell a query.
 cudaError_t launch_fill(const GridDesc& d, int method, const AxisTables& lat, const AxisTables& lon, int64_t row_begin,
-                        int64_t row_end, void* out, int64_t out_ld, cudaStream_t st, LaunchInfo* info);
+                        int64_t row_end, void* out, int64_t out_ld, int fill, cudaStream_t st, LaunchInfo* info);
 
 // metrics.cu -- MAE / RMSE / Max / NaN count of est against truth (error_calculator.cpp:5-45).
 // scratch: device buffer of metrics_scratch_bytes(); result5 (device): {sum|d|, sum d^2, max|d|, #NaN, #compared}.

@@ -453,9 +453,9 @@ static cudaError_t launch_lattice_t(const GridDesc& d, int method, const AxisTab
         if (method == BILINEAR) return launch_tiled<T, BILINEAR>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
         if (method == CUBIC) return launch_tiled<T, CUBIC>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
     }
-    if (fill && !sel) {
+    if (!sel && (fill || method == KRIGING || method == NN || method == IDW)) {
         static const bool v0 = getenv("AUVI_FILL_V0") != nullptr;        // A-B measurements only
-        if (!v0) return launch_fill(d, method, lat, lon, row_begin, row_end, out, out_ld, st, info);
+        if (!v0) return launch_fill(d, method, lat, lon, row_begin, row_end, out, out_ld, fill, st, info);
     }
 #define AUVI_CASE(M)                                                                                         \
     case M:                                                                                                  \
