@@ -556,3 +556,54 @@ def test_fill_tiled_equals_exact_path_on_whole_grids(auvi, torch, frac, dtype_na
             err = (a[ok].double() - b[ok].double()).abs() - 1e-5 * b[ok].double().abs() * (meth == auvi.IDW or dtype_name == "f32")
             assert float(err.max()) <= tol, (auvi.METHOD_NAMES[meth], float(err.max()))
     g.close()
+
+
+def test_config4_full_size_strips_against_exact_path(auvi, torch):
+    """BASELINE config 4 at its stated size -- 65536 x 65536 FP32, 70 % mask drawn by the device hash -- filled by the
+    tiled kernel in ONE launch (4.29 G cells: every flat index beyond 2^31 is exercised), then row strips spread over the
+    grid (first rows, around 2^31 / n_lon, last rows) are recomputed by the per-query exact path and compared:
+    NN bit for bit, IDW within the north-star tolerance; valid cells pass through; no NaN remains."""
+    n = 65536
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 * (1 << 30):
+        pytest.skip("needs ~40 GB of device memory")
+    z = torch.empty((n, n), dtype=torch.float32, device="cuda")
+    i = torch.arange(n, device="cuda", dtype=torch.float64) * (100.0 / (n - 1))
+    base = -(10.0 + 2.0 * i)[None, :]
+    gx = ((i - 75.0) ** 2)[None, :]
+    for r in range(0, n, 2048):
+        j = i[r:r + 2048]
+        z[r:r + 2048] = (base + 100.0 * torch.exp(-(gx + ((j - 50.0) ** 2)[:, None]) / 450.0)).float()
+    truth_strips = {}
+    strips = [0, 4096 - 32, 32768 - 7, 32768 + 1000, n - 64]
+    for r in strips:
+        truth_strips[r] = z[r:r + 64].clone()
+    g = auvi.Grid(adopt=dict(ptr=z.data_ptr(), dtype=auvi.F32, n_lat=n, n_lon=n, ld=n, row0=0, rows=n, keep=z),
+                  min_lon=100.0, max_lon=110.0, min_lat=-10.0, max_lat=0.0)
+    n_masked = g.mask_hash(0.70, seed=42)
+    assert abs(n_masked / (n * n) - 0.70) < 1e-3
+    st = torch.cuda.current_stream().cuda_stream
+    out = torch.empty((n, n), dtype=torch.float32, device="cuda")
+    ref = torch.empty((64, n), dtype=torch.float32, device="cuda")
+    sel = torch.empty((64 * n, 9), dtype=torch.int32, device="cuda")
+    lon_ok = torch.from_numpy(ob.node_axis(100.0, 110.0, n) <= 110.0).cuda()
+    lat_ax_ok = ob.node_axis(-10.0, 0.0, n) <= 0.0
+    for meth in (auvi.NN, auvi.IDW):
+        g.lattice_device(meth, auvi.AXIS_NODES, 1, 1, 1, 0, n, out.data_ptr(), n, None, st)
+        torch.cuda.synchronize()
+        for r in strips:
+            g.lattice_device(meth, auvi.AXIS_NODES, 1, 1, 1, r, r + 64, ref.data_ptr(), n, sel.data_ptr(), st)
+            torch.cuda.synchronize()
+            got = out[r:r + 64]
+            masked = torch.isnan(z[r:r + 64])
+            assert torch.equal(got[~masked], truth_strips[r][~masked])          # pass-through
+            assert torch.equal(torch.isnan(got), torch.isnan(ref))
+            inb = torch.from_numpy(lat_ax_ok[r:r + 64]).cuda()[:, None] & lon_ok[None, :]
+            assert not bool(torch.isnan(got[inb]).any())
+            ok = ~torch.isnan(got)
+            if meth == auvi.NN:
+                assert torch.equal(got[ok], ref[ok])
+            else:
+                err = (got[ok].double() - ref[ok].double()).abs() - 1e-5 * ref[ok].double().abs()
+                assert float(err.max()) <= 1e-3
+    g.close()
