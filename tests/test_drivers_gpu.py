@@ -82,3 +82,39 @@ def test_test_interpolation_runs_unchanged(tmp_path):
         assert a == b, tag
     rows = list(csv.reader(open(tmp_path / "C:" / "College" / "EdgeComputing" / "results" / "TestingResults1.csv")))
     assert len(rows) == 42
+
+
+def test_gebco_gapfill_cpp_driver_reproduces_the_golden_rows(tmp_path):
+    """host/gebco_gapfill.cpp: NetCDF tile -> device grid -> seeded removal -> fill -> device metrics, all through the
+    C ABI from C++.  Its result rows must carry the MAE / RMSE / Max the unmodified reference computes for the same
+    tile and fraction (tests/golden/golden_metrics.json, 'computed')."""
+    import json
+    from scipy.io import netcdf_file
+    from oracle import binding as ob
+    exe = _need("gebco_gapfill")
+    name, frac = "mid_atlantic", 0.5
+    z, m = ob.load_tile(name)
+    nc = str(tmp_path / "tile.nc")
+    f = netcdf_file(nc, "w", version=1)
+    f.createDimension("lat", m["n_lat"]); f.createDimension("lon", m["n_lon"])
+    v = f.createVariable("lat", "d", ("lat",)); v[:] = np.linspace(m["min_lat"], m["max_lat"], m["n_lat"])
+    v = f.createVariable("lon", "d", ("lon",)); v[:] = np.linspace(m["min_lon"], m["max_lon"], m["n_lon"])
+    v = f.createVariable("elevation", "h", ("lat", "lon")); v[:] = z[::-1].astype(np.int16)   # file order: before the flip
+    f.close()
+    out = subprocess.run([exe, nc, str(frac), repr(m["min_lon"]), repr(m["max_lon"]), repr(m["min_lat"]), repr(m["max_lat"])],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    rows = {r[1]: r for r in csv.reader(out.stdout.splitlines()) if r and r[0] == "GPU"}
+    assert set(rows) == {"Bilinear", "Cubic", "Kriging", "Nearest", "IDW"}
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_metrics.json")))["computed"][f"{name}@{frac:.2f}"]
+    for meth in ("Bilinear", "Cubic", "Kriging"):
+        r, g = rows[meth], gold[meth.lower()]
+        assert int(r[2]) == z.size and int(r[3]) == g["n"]
+        np.testing.assert_allclose([float(r[6]), float(r[7]), float(r[8])], [g["mae"], g["rmse"], g["max"]], rtol=1e-8)
+        assert f"{meth}: {g['n_nan']} NaN outputs" in out.stderr
+    # a missing file and a non-NetCDF file fail with the reference's convention: message + non-zero status
+    bad = subprocess.run([exe, str(tmp_path / "nope.nc"), "0.1", "0", "1", "0", "1"], capture_output=True, text=True)
+    assert bad.returncode != 0 and "unable to open" in bad.stderr
+    (tmp_path / "junk.nc").write_bytes(b"not a netcdf file at all" * 8)
+    bad = subprocess.run([exe, str(tmp_path / "junk.nc"), "0.1", "0", "1", "0", "1"], capture_output=True, text=True)
+    assert bad.returncode != 0 and "NetCDF" in bad.stderr
