@@ -602,6 +602,109 @@ int auvi_grid_create_raw(const void* host_raw, int nc_type, int big_endian, int 
     return 0;
 }
 
+int auvi_csv_dims(const char* text, int64_t n_bytes, int64_t* n_rows, int64_t* n_cols) {
+    if (!text || n_bytes < 0) return fail("null CSV text");
+    while (n_bytes > 0 && (text[n_bytes - 1] == '\n' || text[n_bytes - 1] == '\r' || text[n_bytes - 1] == ' ')) --n_bytes;
+    if (n_bytes == 0) return fail("Grid data is empty.");                       // test_gebco.cpp:127-128
+    int64_t cols = 1, rows = 1;
+    const char* first_nl = static_cast<const char*>(memchr(text, '\n', static_cast<size_t>(n_bytes)));
+    const int64_t first_len = first_nl ? first_nl - text : n_bytes;
+    for (int64_t k = 0; k < first_len; ++k) cols += text[k] == ',';
+    for (const char* p = first_nl; p; p = static_cast<const char*>(memchr(p + 1, '\n', static_cast<size_t>(text + n_bytes - p - 1)))) ++rows;
+    if (n_rows) *n_rows = rows;
+    if (n_cols) *n_cols = cols;
+    return 0;
+}
+
+int auvi_grid_create_csv(const char* text, int64_t n_bytes, int dtype, double min_lon, double max_lon, double min_lat,
+                         double max_lat, int device, auvi_grid** out) {
+    if (!out) return fail("null output handle");
+    *out = nullptr;
+    int64_t n_rows = 0, n_cols = 0;
+    if (auvi_csv_dims(text, n_bytes, &n_rows, &n_cols)) return 1;
+    while (n_bytes > 0 && (text[n_bytes - 1] == '\n' || text[n_bytes - 1] == '\r' || text[n_bytes - 1] == ' ')) --n_bytes;
+    if (auvi_device_count() <= 0) return fail("no CUDA device: libauvi has no CPU fallback");
+    auvi_grid* g = new (std::nothrow) auvi_grid;
+    if (!g) return fail("out of host memory");
+    if (fill_desc(g->d, dtype, n_rows, n_cols, min_lon, max_lon, min_lat, max_lat)) { delete g; return 1; }
+    g->device = device;
+    const size_t es = dtype == AUVI_F64 ? 8 : 4;
+    const int64_t ld = (n_cols * es + 15) / 16 * 16 / es, n_fields = n_rows * n_cols, n_text = n_bytes + 1;
+    const size_t n_blocks = csv_block_count(n_text);
+    // device scratch: text (+ the final newline), per-block counts and offsets, delimiter positions, slow-field list
+    struct Blk { void* p = nullptr; size_t bytes = 0; };
+    Blk b_text{nullptr, static_cast<size_t>(n_text)}, b_counts{nullptr, n_blocks * sizeof(int)}, b_off{nullptr, n_blocks * sizeof(int64_t)},
+        b_pos{nullptr, static_cast<size_t>(n_fields) * sizeof(int64_t)}, b_slow{nullptr, static_cast<size_t>(n_fields) * sizeof(int64_t)},
+        b_misc{nullptr, 4096};
+    Blk* all[] = {&b_text, &b_counts, &b_off, &b_pos, &b_slow, &b_misc};
+    auto release = [&](bool also_grid) {
+        for (Blk* b : all) if (b->p) cached_free(b->p, b->bytes, device);
+        if (also_grid) { if (g->owned) cached_free(g->owned, g->owned_bytes, device); delete g; }
+    };
+    cudaError_t e = cudaSetDevice(device);
+    g->owned_bytes = static_cast<size_t>(ld) * n_rows * es;
+    if (e == cudaSuccess) e = cached_malloc(&g->owned, g->owned_bytes, device);
+    for (Blk* b : all) if (e == cudaSuccess) e = cached_malloc(&b->p, b->bytes, device);
+    if (e != cudaSuccess) { release(true); return fail_cuda("CSV scratch allocation", e); }
+    char* d_text = static_cast<char*>(b_text.p);
+    int64_t* d_total = static_cast<int64_t*>(b_misc.p);
+    unsigned* d_status = reinterpret_cast<unsigned*>(d_total + 1);
+    unsigned long long* d_nslow = reinterpret_cast<unsigned long long*>(d_total + 2);
+    const char nl = '\n';
+    e = cudaMemcpy(d_text, text, static_cast<size_t>(n_bytes), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_text + n_bytes, &nl, 1, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(b_misc.p, 0, 64);
+    if (e == cudaSuccess) e = launch_csv_index(d_text, n_text, static_cast<int*>(b_counts.p), static_cast<int64_t*>(b_off.p), d_total,
+                                               static_cast<int64_t*>(b_pos.p), n_fields, nullptr);
+    int64_t h_misc[3] = {0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(h_misc, b_misc.p, 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { release(true); return fail_cuda("CSV delimiter index", e); }
+    if (h_misc[0] != n_fields) {
+        release(true);
+        return fail("CSV rows do not all have the same number of fields (" + std::to_string(h_misc[0]) + " fields for " +
+                    std::to_string(n_rows) + " x " + std::to_string(n_cols) + ")");
+    }
+    e = launch_csv_parse(d_text, static_cast<const int64_t*>(b_pos.p), n_fields, static_cast<int>(n_cols), g->owned, ld, dtype, d_status,
+                         d_nslow, static_cast<int64_t*>(b_slow.p), n_fields, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(h_misc, b_misc.p, 24, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { release(true); return fail_cuda("CSV parse", e); }
+    g_launches.fetch_add(4);
+    const unsigned status = static_cast<unsigned>(h_misc[1] & 0xffffffff);
+    if (status & 1u) { release(true); return fail("CSV rows do not all have the same number of fields"); }
+    if (status & 2u) { release(true); return fail("CSV holds a field that is not a number (or an empty field)"); }
+    const int64_t n_slow = h_misc[2];
+    if (n_slow > 0) {
+        // fields beyond the exact fast path (more than 19 digits, |exponent| > 22 ...): strtod on the host, like the reference
+        std::vector<int64_t> idx(static_cast<size_t>(n_slow)), pos(static_cast<size_t>(n_fields));
+        std::vector<double> val(static_cast<size_t>(n_slow));
+        e = cudaMemcpy(idx.data(), b_slow.p, sizeof(int64_t) * n_slow, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(pos.data(), b_pos.p, sizeof(int64_t) * n_fields, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) {
+            for (int64_t k = 0; k < n_slow; ++k) {
+                const int64_t f = idx[k], a = f ? pos[f - 1] + 1 : 0, b = pos[f];
+                const std::string cell(text + a, static_cast<size_t>((b < n_bytes ? b : n_bytes) - a));
+                val[k] = std::strtod(cell.c_str(), nullptr);
+            }
+            void* d_val = nullptr;
+            e = cached_malloc(&d_val, sizeof(double) * n_slow, device);
+            if (e == cudaSuccess) e = cudaMemcpy(d_val, val.data(), sizeof(double) * n_slow, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = launch_csv_patch(g->owned, ld, static_cast<int>(n_cols), dtype, static_cast<const int64_t*>(b_slow.p),
+                                                       static_cast<const double*>(d_val), n_slow, nullptr);
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            if (d_val) cached_free(d_val, sizeof(double) * n_slow, device);
+            g_launches.fetch_add(1);
+        }
+        if (e != cudaSuccess) { release(true); return fail_cuda("CSV slow-field patch", e); }
+    }
+    e = cudaDeviceSynchronize();
+    release(false);
+    if (e != cudaSuccess) { cudaFree(g->owned); delete g; return fail_cuda("CSV parse", e); }
+    g->d.z = g->owned; g->d.ld = ld; g->d.row0 = 0; g->d.rows = g->d.n_lat;
+    if (make_streams(g)) { auvi_grid_destroy(g); return 2; }
+    *out = g;
+    return 0;
+}
+
 int auvi_grid_mask_cells(auvi_grid* g, const int64_t* host_flat_idx, int64_t n, void* host_truth) {
     if (!g) return fail("null grid handle");
     if (n < 0) return fail("negative cell count");

@@ -125,4 +125,215 @@ cudaError_t launch_mask_hash(const GridDesc& d, double fraction, uint64_t seed, 
     return cudaGetLastError();
 }
 
+
+// ---- CSV matrix text -> grid, parsed on the device -------------------------------------------------------------
+// The reference's driver reads its grids from CSV text with getline + stod into a vector<vector<double>>
+// (test_gebco.cpp:19-40, test_interpolation.cpp readGridCSV).  Here the text is uploaded as it is and parsed in four
+// passes: (1) delimiters (',' and '\n') counted per 4 KiB block, (2) exclusive scan of the counts, (3) the position of
+// every delimiter written out, (4) one thread per field converts its characters.  Decimal -> double is Clinger's fast
+// path: up to 15 significant digits and a power of ten up to 10^22 are exact in FP64, so one multiplication or division
+// is correctly rounded -- the value stod returns.  Fields outside the fast path (more digits, larger exponents) are
+// flagged and converted on the host with strtod by the caller (api.cu), so every value equals the reference's.
+namespace csv {
+
+constexpr int kBlockBytes = 4096, kThreads = 256, kPerThread = kBlockBytes / kThreads;
+
+__device__ __forceinline__ bool is_delim(char ch) { return ch == ',' || ch == '\n'; }
+
+__global__ void __launch_bounds__(kThreads)
+count_kernel(const char* __restrict__ text, int64_t n, int* __restrict__ counts) {
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * kBlockBytes + threadIdx.x * kPerThread;
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k) c += (base + k < n) && is_delim(text[base + k]);
+    __shared__ int warp_sum[kThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < kThreads / 32; ++w) t += warp_sum[w];
+        counts[blockIdx.x] = t;
+    }
+}
+
+// one CTA walks the block counts in slices of 1024 with a running carry: offsets[b] = sum of counts before b
+__global__ void __launch_bounds__(1024)
+scan_kernel(const int* __restrict__ counts, int64_t n_blocks, int64_t* __restrict__ offsets, int64_t* __restrict__ total) {
+    __shared__ int64_t warp_tot[32];
+    __shared__ int64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t b0 = 0; b0 < n_blocks; b0 += 1024) {
+        const int64_t b = b0 + threadIdx.x;
+        const int64_t v = b < n_blocks ? counts[b] : 0;
+        int64_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int64_t w = warp_tot[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int64_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            warp_tot[lane] = wi - w;                                // exclusive over warps
+        }
+        __syncthreads();
+        const int64_t carry = carry_s;
+        if (b < n_blocks) offsets[b] = carry + warp_tot[warp] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_tot[warp] + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry_s;
+}
+
+__global__ void __launch_bounds__(kThreads)
+positions_kernel(const char* __restrict__ text, int64_t n, const int64_t* __restrict__ offsets, int64_t* __restrict__ pos,
+                 int64_t max_fields) {
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * kBlockBytes + threadIdx.x * kPerThread;
+    int mine = 0;
+    bool d[kPerThread];
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k) { d[k] = (base + k < n) && is_delim(text[base + k]); mine += d[k]; }
+    // exclusive prefix of `mine` over the CTA
+    __shared__ int warp_sum[kThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += warp_sum[w];
+    int64_t at = offsets[blockIdx.x] + before + incl - mine;
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k)
+        if (d[k]) { if (at < max_fields) pos[at] = base + k; ++at; }
+}
+
+// status bits per run: 1 = a row does not have n_cols fields, 2 = a field that is not a number, 4 = slow fields exist
+template <typename T>
+__global__ void __launch_bounds__(256)
+parse_kernel(const char* __restrict__ text, const int64_t* __restrict__ pos, int64_t n_fields, int n_cols, T* __restrict__ out,
+             int64_t ld, unsigned* __restrict__ status, unsigned long long* __restrict__ n_slow, int64_t* __restrict__ slow_idx,
+             int64_t slow_cap) {
+    const double p10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16,
+                            1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+    for (int64_t f = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; f < n_fields; f += static_cast<int64_t>(gridDim.x) * 256) {
+        int64_t a = f ? pos[f - 1] + 1 : 0, b = pos[f];            // [a, b) = the field's characters
+        const bool row_end = text[b] == '\n';
+        if (row_end != ((f + 1) % n_cols == 0)) { atomicOr(status, 1u); continue; }
+        while (a < b && (text[a] == ' ' || text[a] == '\t')) ++a;
+        while (b > a && (text[b - 1] == ' ' || text[b - 1] == '\t' || text[b - 1] == '\r')) --b;
+        double v = 0.0;
+        bool ok = a < b, slow = false;
+        if (ok) {
+            bool neg = false;
+            int64_t q = a;
+            if (text[q] == '-' || text[q] == '+') { neg = text[q] == '-'; ++q; }
+            const int len = static_cast<int>(b - q);
+            auto lower = [&](int64_t at) { const char ch = text[at]; return (ch >= 'A' && ch <= 'Z') ? static_cast<char>(ch + 32) : ch; };
+            if (len == 3 && lower(q) == 'n' && lower(q + 1) == 'a' && lower(q + 2) == 'n') v = qnan();
+            else if ((len == 3 || len == 8) && lower(q) == 'i' && lower(q + 1) == 'n' && lower(q + 2) == 'f') v = __longlong_as_double(0x7ff0000000000000LL);
+            else {
+                uint64_t m = 0;
+                int digits = 0, seen = 0, e10 = 0;
+                bool dot = false;
+                for (; q < b; ++q) {
+                    const char ch = text[q];
+                    if (ch >= '0' && ch <= '9') {
+                        ++seen;
+                        if (m || ch != '0') {
+                            if (digits < 19) { m = m * 10 + static_cast<uint64_t>(ch - '0'); ++digits; if (dot) --e10; }
+                            else { slow = true; if (!dot) ++e10; }
+                        } else if (dot) --e10;
+                    } else if (ch == '.' && !dot) dot = true;
+                    else break;
+                }
+                if (!seen) ok = false;
+                if (ok && q < b && (text[q] == 'e' || text[q] == 'E')) {
+                    ++q;
+                    bool eneg = false;
+                    if (q < b && (text[q] == '-' || text[q] == '+')) { eneg = text[q] == '-'; ++q; }
+                    int e = 0, ed = 0;
+                    for (; q < b && text[q] >= '0' && text[q] <= '9'; ++q) { if (e < 100000) e = e * 10 + (text[q] - '0'); ++ed; }
+                    if (!ed) ok = false;
+                    e10 += eneg ? -e : e;
+                }
+                if (ok && q != b) ok = false;                       // trailing characters: not a plain number
+                if (ok) {
+                    if (m == 0) v = 0.0;
+                    else if (!slow && m < (1ull << 53) && e10 >= -22 && e10 <= 22)
+                        v = e10 < 0 ? ddiv(static_cast<double>(m), p10[-e10]) : dmul(static_cast<double>(m), p10[e10]);
+                    else if (!slow && m < (1ull << 53) && e10 > 22 && e10 <= 22 + 15 && static_cast<double>(m) * p10[e10 - 22] < 9007199254740992.0)
+                        v = dmul(dmul(static_cast<double>(m), p10[e10 - 22]), p10[22]);   // still exact: m * 10^(e-22) < 2^53
+                    else slow = true;
+                }
+            }
+            if (neg) v = -v;
+        }
+        if (!ok) { atomicOr(status, 2u); continue; }
+        const int64_t r = f / n_cols, c = f % n_cols;
+        if (slow) {
+            atomicOr(status, 4u);
+            const unsigned long long slot = atomicAdd(n_slow, 1ull);
+            if (static_cast<int64_t>(slot) < slow_cap) slow_idx[slot] = f;
+            v = qnan();
+        }
+        out[r * ld + c] = static_cast<T>(v);
+    }
+}
+
+template <typename T>
+__global__ void patch_kernel(T* __restrict__ out, int64_t ld, int n_cols, const int64_t* __restrict__ idx,
+                             const double* __restrict__ val, int64_t n) {
+    for (int64_t k = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; k < n; k += static_cast<int64_t>(gridDim.x) * 256) {
+        const int64_t f = idx[k];
+        out[(f / n_cols) * ld + f % n_cols] = static_cast<T>(val[k]);
+    }
+}
+
+}  // namespace csv
+
+size_t csv_block_count(int64_t n_bytes) { return static_cast<size_t>((n_bytes + csv::kBlockBytes - 1) / csv::kBlockBytes); }
+
+cudaError_t launch_csv_index(const char* text, int64_t n_bytes, int* counts, int64_t* offsets, int64_t* total, int64_t* pos,
+                             int64_t max_fields, cudaStream_t st) {
+    const unsigned blocks = static_cast<unsigned>(csv_block_count(n_bytes));
+    csv::count_kernel<<<blocks, csv::kThreads, 0, st>>>(text, n_bytes, counts);
+    csv::scan_kernel<<<1, 1024, 0, st>>>(counts, blocks, offsets, total);
+    csv::positions_kernel<<<blocks, csv::kThreads, 0, st>>>(text, n_bytes, offsets, pos, max_fields);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_csv_parse(const char* text, const int64_t* pos, int64_t n_fields, int n_cols, void* out, int64_t ld, int dtype,
+                             unsigned* status, unsigned long long* n_slow, int64_t* slow_idx, int64_t slow_cap, cudaStream_t st) {
+    const int blocks = grid_blocks(n_fields);
+    if (dtype == DT_F64)
+        csv::parse_kernel<double><<<blocks, 256, 0, st>>>(text, pos, n_fields, n_cols, static_cast<double*>(out), ld, status, n_slow, slow_idx, slow_cap);
+    else
+        csv::parse_kernel<float><<<blocks, 256, 0, st>>>(text, pos, n_fields, n_cols, static_cast<float*>(out), ld, status, n_slow, slow_idx, slow_cap);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_csv_patch(void* out, int64_t ld, int n_cols, int dtype, const int64_t* idx, const double* val, int64_t n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const int blocks = grid_blocks(n);
+    if (dtype == DT_F64) csv::patch_kernel<double><<<blocks, 256, 0, st>>>(static_cast<double*>(out), ld, n_cols, idx, val, n);
+    else csv::patch_kernel<float><<<blocks, 256, 0, st>>>(static_cast<float*>(out), ld, n_cols, idx, val, n);
+    return cudaGetLastError();
+}
+
 }  // namespace auvi

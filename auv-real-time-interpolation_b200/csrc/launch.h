@@ -84,6 +84,14 @@ cudaError_t launch_decode_raw(const void* raw, int nc_type, int big_endian, int 
                               int n_lat, int n_lon, void* out, int64_t ld, int dtype, cudaStream_t st);
 cudaError_t launch_mask_cells(const GridDesc& d, const int64_t* idx, int64_t n, void* truth, cudaStream_t st);
 cudaError_t launch_mask_hash(const GridDesc& d, double fraction, uint64_t seed, unsigned long long* n_masked, cudaStream_t st);
+// CSV matrix text on the device: delimiter index (counts per 4 KiB block -> scan -> positions), then one thread per field.
+size_t csv_block_count(int64_t n_bytes);
+cudaError_t launch_csv_index(const char* text, int64_t n_bytes, int* counts, int64_t* offsets, int64_t* total, int64_t* pos,
+                             int64_t max_fields, cudaStream_t st);
+cudaError_t launch_csv_parse(const char* text, const int64_t* pos, int64_t n_fields, int n_cols, void* out, int64_t ld, int dtype,
+                             unsigned* status, unsigned long long* n_slow, int64_t* slow_idx, int64_t slow_cap, cudaStream_t st);
+cudaError_t launch_csv_patch(void* out, int64_t ld, int n_cols, int dtype, const int64_t* idx, const double* val, int64_t n,
+                             cudaStream_t st);
 
 // Encodes a 2-D tiled tensor map over the grid slab; returns false when TMA cannot address it.
 bool make_grid_tensor_map(const GridDesc& d, int box_w, int box_h, CUtensorMap* out);

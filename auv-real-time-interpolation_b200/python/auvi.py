@@ -46,6 +46,8 @@ SYMBOLS = {
     "auvi_legacy_choice": (_i32, [_i64, _i64, C.c_uint32, _vp]),
     "auvi_grid_create_raw": (_i32, [_vp, _i32, _i32, _i32, _dbl, _dbl, _i32, _i64, _i64, _dbl, _dbl, _dbl, _dbl, _i32,
                                     C.POINTER(_vp)]),
+    "auvi_csv_dims": (_i32, [C.c_char_p, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
+    "auvi_grid_create_csv": (_i32, [C.c_char_p, _i64, _i32, _dbl, _dbl, _dbl, _dbl, _i32, C.POINTER(_vp)]),
     "auvi_grid_mask_cells": (_i32, [_vp, _vp, _i64, _vp]),
     "auvi_grid_mask_hash": (_i32, [_vp, _dbl, C.c_uint64, C.POINTER(_i64), _vp]),
     "auvi_grid_read": (_i32, [_vp, _i64, _i64, _vp]),
@@ -142,6 +144,19 @@ class Grid:
         raw = (C.c_char * (v.n_elems * v.elem_bytes)).from_buffer_copy(image, v.data_offset)
         _check(load().auvi_grid_create_raw(raw, v.nc_type, 1, int(flip_rows), v.scale_factor, v.add_offset, dtype,
                                            self.n_lat, self.n_lon, *bounds, device, C.byref(self._h)))
+        return self
+
+    @classmethod
+    def from_csv(cls, text: bytes, bounds, dtype=F64, device=0):
+        """CSV matrix text (readGridCSV's input, test_gebco.cpp:19-40) -> device grid, parsed on the GPU."""
+        self = cls.__new__(cls)
+        self._h = _vp()
+        self.bounds = tuple(bounds)
+        self.dtype = dtype
+        r, c = _i64(), _i64()
+        _check(load().auvi_csv_dims(text, len(text), C.byref(r), C.byref(c)))
+        self.n_lat, self.n_lon = r.value, c.value
+        _check(load().auvi_grid_create_csv(text, len(text), dtype, *bounds, device, C.byref(self._h)))
         return self
 
     def mask_cells(self, flat_idx, want_truth=True):

@@ -138,6 +138,13 @@ int auvi_legacy_choice(int64_t total, int64_t n, uint32_t seed, int64_t* out_idx
 int auvi_grid_create_raw(const void* host_raw, int nc_type, int big_endian, int flip_rows, double scale, double offset,
                          int dtype, int64_t n_lat, int64_t n_lon, double min_lon, double max_lon, double min_lat,
                          double max_lat, int device, auvi_grid** out);
+/* A grid from CSV matrix text (one row per latitude, comma separated, "nan" for missing cells: reduced_data.csv of
+ * subset_bathymetry.py:78-85, the files readGridCSV parses, test_gebco.cpp:19-40).  The text is uploaded as it is and
+ * parsed on the device; every value equals what std::stod returns for the cell.  Rows must have equal field counts.
+ * auvi_csv_dims is host only. */
+int auvi_csv_dims(const char* text, int64_t n_bytes, int64_t* n_rows, int64_t* n_cols);
+int auvi_grid_create_csv(const char* text, int64_t n_bytes, int dtype, double min_lon, double max_lon, double min_lat,
+                         double max_lat, int device, auvi_grid** out);
 /* Remove cells: host_flat_idx[k] = row*n_lon+col (subset_bathymetry.py:39).  The cells become NaN in the grid's own
  * storage (also for adopted memory); host_truth (optional, n elements of the grid's dtype) receives their former values
  * in list order -- the third column of reference_missing.csv (:49-56).  Cells outside a slab are skipped (truth NaN). */

@@ -88,3 +88,18 @@ def test_netcdf3_on_the_reference_tiles():
         assert (v.shape[0], v.shape[1]) == e.shape and v.nc_type == 3
         assert np.array_equal(np.frombuffer(img, dtype=">i2", count=v.n_elems, offset=v.data_offset).reshape(e.shape), e)
         assert np.array_equal(auvi.netcdf3_read_f64(img, "lat"), nc.variables["lat"][:])
+
+
+def test_csv_dims_host_only():
+    import ctypes as C
+    lib = auvi.load()
+    def dims(text):
+        r, c = C.c_int64(), C.c_int64()
+        rc = lib.auvi_csv_dims(text, len(text), C.byref(r), C.byref(c))
+        return rc, r.value, c.value
+    assert dims(b"1,2,3\n4,5,6\n") == (0, 2, 3)
+    assert dims(b"1,2,3\r\n4,5,6") == (0, 2, 3)                 # CRLF, no trailing newline
+    assert dims(b"-5559.0\n") == (0, 1, 1)
+    assert dims(b"1,nan\n2,3\n\n\n") == (0, 2, 2)               # trailing blank lines are not rows
+    rc, _, _ = dims(b"\n\n")
+    assert rc != 0 and b"Grid data is empty" in lib.auvi_last_error()

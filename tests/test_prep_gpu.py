@@ -112,3 +112,55 @@ def test_mask_hash_is_slab_invariant(auvi, torch):
     other = base.clone()
     g = grid_of(other, 0); g.mask_hash(0.7, seed=43); g.close()
     assert not torch.equal(torch.isnan(other), torch.isnan(whole))
+
+
+def _csv_text(z, fmt):
+    return ("\n".join(",".join("nan" if np.isnan(v) else fmt(v) for v in row) for row in z) + "\n").encode()
+
+
+@pytest.mark.parametrize("style", ["int", "g6", "repr", "exp", "crlf_noeol", "long"])
+def test_csv_parsed_on_device_equals_stod(auvi, style):
+    """auvi_grid_create_csv against Python's float() (correctly rounded, as glibc strtod / std::stod) cell by cell:
+    GEBCO integers, the 6-significant-digit text of generate_csv_grids.cpp, 17-digit repr (beyond the exact fast
+    path for most cells: host strtod patch), exponent forms, CRLF without a final newline, >19-digit fields."""
+    rng = np.random.RandomState(5)
+    n_lat, n_lon = 211, 173
+    z = rng.uniform(-11000.0, 500.0, size=(n_lat, n_lon))
+    z.ravel()[rng.choice(z.size, 4000, replace=False)] = np.nan
+    fmt = {"int": lambda v: str(int(round(v))), "g6": lambda v: "%.6g" % v, "repr": lambda v: repr(float(v)),
+           "exp": lambda v: "%.9e" % (v * 1e-12), "crlf_noeol": lambda v: "%.4f" % v,
+           "long": lambda v: "%.25f" % v}[style]
+    text = _csv_text(z, fmt)
+    if style == "crlf_noeol":
+        text = text.replace(b"\n", b"\r\n")[:-2]
+    want = np.array([[float(c) for c in line.split(",")] for line in text.decode().replace("\r", "").strip().split("\n")])
+    g = auvi.Grid.from_csv(text, (0.0, 1.0, 0.0, 1.0))
+    assert (g.n_lat, g.n_lon) == (n_lat, n_lon)
+    assert bits_equal(g.read(), want), style
+    g.close()
+    g32 = auvi.Grid.from_csv(text, (0.0, 1.0, 0.0, 1.0), dtype=auvi.F32)
+    assert bits_equal(g32.read().astype(np.float64), want.astype(np.float32).astype(np.float64))
+    g32.close()
+
+
+def test_csv_grid_runs_the_grid_b_case(auvi):
+    """reduced_data.csv of a fixture case as text -> device grid: identical to the host-uploaded grid."""
+    case = ob.masked_case("mid_atlantic", 0.5)
+    text = _csv_text(case["z"], lambda v: repr(float(v)))                    # pandas to_csv writes -5559.0
+    g = auvi.Grid.from_csv(text, case["bounds"])
+    assert bits_equal(g.read(), case["z"])
+    h = auvi.Grid(case["z"], *case["bounds"])
+    for meth in (auvi.CUBIC, auvi.KRIGING):
+        assert bits_equal(g.lattice(meth, auvi.AXIS_NODES, 1, 1, fill=1), h.lattice(meth, auvi.AXIS_NODES, 1, 1, fill=1))
+    g.close(); h.close()
+
+
+def test_csv_errors(auvi):
+    with pytest.raises(auvi.AuviError, match="same number of fields"):
+        auvi.Grid.from_csv(b"1,2,3\n4,5\n6,7,8\n", (0.0, 1.0, 0.0, 1.0))
+    with pytest.raises(auvi.AuviError, match="same number of fields"):
+        auvi.Grid.from_csv(b"1,2,3\n4,5,6,7\n8,9\n", (0.0, 1.0, 0.0, 1.0))     # right total, wrong rows
+    with pytest.raises(auvi.AuviError, match="not a number"):
+        auvi.Grid.from_csv(b"1,2\n3,abc\n", (0.0, 1.0, 0.0, 1.0))
+    with pytest.raises(auvi.AuviError, match="not a number"):
+        auvi.Grid.from_csv(b"1,,2\n3,4,5\n", (0.0, 1.0, 0.0, 1.0))             # empty field
