@@ -395,6 +395,8 @@ def main():
     # ---- N > 1: the only collective on the path -- gathering output shards to one consumer (not in `value`) ----
     gather = None
     if dist is not None:
+        step()                                                      # `out` holds the bicubic result again (extras reused it)
+        torch.cuda.synchronize()
         g_rows = min(my_rows, (4 << 30) // (out_ld * 4))            # bounded: at most 4 GiB per rank
         sendbuf = out[:g_rows]
         recv = [torch.empty_like(sendbuf) for _ in range(world)] if rank == 0 else None
