@@ -47,6 +47,7 @@ constexpr int kFRedoMax = 128;
 constexpr int kFReplayMax = 256;                // near-tie queries replayed with square roots (more: literal path)
 constexpr int kFSq = 3;                        // squared-offset tables cover |offset| <= kFSq
 constexpr int kFNear = 8;                      // near path: at most this many candidates, all within the 5 x 5 block
+constexpr int kFUnroll = 3;                    // rings unrolled with their row windows in registers; further rings: rolled loops
 constexpr int kFBinNear = 80;                  // bins 0..79: general path (termination x count); 80..84: near path by count
 constexpr int kFBins = 96;
 
@@ -494,14 +495,14 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const int lj = k / kFW, li = k % kFW;
         const int ci = s.cx[li] - c0, cj = s.cy[lj] - r0;
         const int sh0 = ci - 10, wi = sh0 >> 5, sh = sh0 & 31;
-        uint32_t wt[kMaxRadius + 1], wb[kMaxRadius + 1];
+        uint32_t wt[kFUnroll + 1], wb[kFUnroll + 1];
         const uint32_t w0 = window(cj, wi, sh);
         wt[0] = w0; wb[0] = w0;
         int n = (w0 >> 10) & 1;
         int r_end = kMaxRadius, lr_end = 1;                         // last ring visited; did its left/right pass run?
         bool done = false;
 #pragma unroll
-        for (int r = 1; r <= kMaxRadius; ++r) {
+        for (int r = 1; r <= kFUnroll; ++r) {
             if (!done) {
                 wt[r] = window(cj - r, wi, sh); wb[r] = window(cj + r, wi, sh);
                 const uint32_t tbm = ((2u << (2 * r)) - 1u) << (10 - r);
@@ -515,6 +516,16 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                     n += c;
                     if (n >= 4) { done = true; r_end = r; lr_end = 1; }
                 }
+            }
+        }
+        for (int r = kFUnroll + 1; r <= kMaxRadius && !done; ++r) {   // sparse neighbourhoods: rolled, windows re-read
+            const uint32_t tbm = ((2u << (2 * r)) - 1u) << (10 - r);
+            n += __popc(window(cj - r, wi, sh) & tbm) + __popc(window(cj + r, wi, sh) & tbm);
+            if (n >= 4) { done = true; r_end = r; lr_end = 0; }
+            else {
+                const uint32_t lrm = (1u << (10 - r)) | (1u << (10 + r));
+                for (int dy = -r + 1; dy <= r - 1; ++dy) n += __popc(window(cj + dy, wi, sh) & lrm);
+                if (n >= 4) { done = true; r_end = r; lr_end = 1; }
             }
         }
         if (n > kFNMax) to_literal(k);
@@ -596,12 +607,12 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             lcode[cnt * kFThreads] = static_cast<uint16_t>((dy + 10) * 32 + (dx + 10));
             ++cnt;
         };
-        uint32_t wt[kMaxRadius + 1], wb[kMaxRadius + 1];
+        uint32_t wt[kFUnroll + 1], wb[kFUnroll + 1];
         const uint32_t w0 = window(cj, wi, sh);
         wt[0] = w0; wb[0] = w0;
         if ((w0 >> 10) & 1) push(0, 0, dadd(sqdx(0), sqdy(0)));
 #pragma unroll
-        for (int r = 1; r <= kMaxRadius; ++r) {
+        for (int r = 1; r <= kFUnroll; ++r) {
             if (r <= r_end) {
                 wt[r] = window(cj - r, wi, sh); wb[r] = window(cj + r, wi, sh);
                 const uint32_t tbm = ((2u << (2 * r)) - 1u) << (10 - r);
@@ -633,6 +644,35 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                                 if (wr & rb) push(r, dy, dadd(dxr, dy2));
                             }
                         }
+                    }
+                }
+            }
+        }
+        for (int r = kFUnroll + 1; r <= r_end; ++r) {               // sparse neighbourhoods: the same walk, rolled
+            const uint32_t tbm = ((2u << (2 * r)) - 1u) << (10 - r);
+            const uint32_t top = window(cj - r, wi, sh) & tbm, bot = window(cj + r, wi, sh) & tbm;
+            uint32_t m = top | bot;
+            if (m) {
+                const double dyt = sqdy(-r), dyb = sqdy(r);
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    const double dx2 = sqdx(b - 10);
+                    if ((top >> b) & 1u) push(b - 10, -r, dadd(dx2, dyt));
+                    if ((bot >> b) & 1u) push(b - 10, r, dadd(dx2, dyb));
+                }
+            }
+            if (r < r_end || lr_end) {
+                const uint32_t lb = 1u << (10 - r), rb = 1u << (10 + r);
+                double dxl = 0.0, dxr = 0.0;
+                bool have = false;
+                for (int dy = -r + 1; dy <= r - 1; ++dy) {
+                    const uint32_t wr = window(cj + dy, wi, sh);
+                    if (wr & (lb | rb)) {
+                        if (!have) { dxl = sqdx(-r); dxr = sqdx(r); have = true; }
+                        const double dy2 = sqdy(dy);
+                        if (wr & lb) push(-r, dy, dadd(dxl, dy2));
+                        if (wr & rb) push(r, dy, dadd(dxr, dy2));
                     }
                 }
             }
