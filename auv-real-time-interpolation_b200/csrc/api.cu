@@ -24,6 +24,8 @@
 #include <string>
 #include <vector>
 
+#include <omp.h>
+
 #include "../../include/auvi.h"
 #include "launch.h"
 
@@ -116,12 +118,21 @@ void cached_free(void* p, size_t bytes, int device) {
     cudaFree(p);
 }
 
-constexpr int64_t kPointChunk = 1 << 20;            // queries per pipeline stage (16 MiB in, 8 MiB out)
+constexpr int64_t kPointChunk = 1 << 20;            // most queries per pipeline stage (16 MiB in, 8 MiB out)
+constexpr int64_t kPointChunkMin = 1 << 16;         // smaller batches are cut into ~4 stages so that packing overlaps the copies
 constexpr int64_t kLatticeChunkBytes = 256ll << 20; // device staging per pipeline stage, lattice host form
 
 }  // namespace
 
 int auvi::set_error(const std::string& msg) { return fail(msg); }
+
+struct PointStaging {
+    int device = 0;
+    double* h_in[2] = {nullptr, nullptr};
+    double* h_out[2] = {nullptr, nullptr};
+    double* d_in[2] = {nullptr, nullptr};
+    double* d_out[2] = {nullptr, nullptr};
+};
 
 struct auvi_grid {
     GridDesc d;
@@ -135,6 +146,7 @@ struct auvi_grid {
     double* h_out[2] = {nullptr, nullptr};            // pinned
     double* d_in[2] = {nullptr, nullptr};
     double* d_out[2] = {nullptr, nullptr};
+    PointStaging* staging = nullptr;                  // owner of the four above (process-wide pool)
     // lattice host-form staging
     void* d_rows[2] = {nullptr, nullptr};
     size_t d_rows_bytes = 0;
@@ -247,15 +259,51 @@ struct MetricsScratch {
     }
 };
 
+// Pinned + device staging of the point-list pipeline, kept process-wide: a caller that builds a GridD per batch -- as
+// the reference's drivers do -- should not pin 48 MB of host memory and free it again on every grid.
+std::mutex g_staging_mu;
+std::vector<PointStaging*> g_staging_free;
+
+void release_staging(PointStaging* ps) {
+    for (int k = 0; k < 2; ++k) {
+        if (ps->h_in[k]) cudaFreeHost(ps->h_in[k]);
+        if (ps->h_out[k]) cudaFreeHost(ps->h_out[k]);
+        cudaFree(ps->d_in[k]); cudaFree(ps->d_out[k]);
+    }
+    delete ps;
+}
+
 int ensure_point_staging(auvi_grid* g) {
     if (g->h_in[0]) return 0;
-    for (int k = 0; k < 2; ++k) {
-        AUVI_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g->h_in[k]), sizeof(double) * 2 * kPointChunk, cudaHostAllocDefault));
-        AUVI_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g->h_out[k]), sizeof(double) * kPointChunk, cudaHostAllocDefault));
-        AUVI_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->d_in[k]), sizeof(double) * 2 * kPointChunk));
-        AUVI_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->d_out[k]), sizeof(double) * kPointChunk));
+    PointStaging* ps = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_staging_mu);
+        for (size_t k = 0; k < g_staging_free.size(); ++k)
+            if (g_staging_free[k]->device == g->device) { ps = g_staging_free[k]; g_staging_free.erase(g_staging_free.begin() + k); break; }
     }
+    if (!ps) {
+        ps = new (std::nothrow) PointStaging;
+        if (!ps) return fail("out of host memory");
+        ps->device = g->device;
+        cudaError_t e = cudaSuccess;
+        for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+            e = cudaHostAlloc(reinterpret_cast<void**>(&ps->h_in[k]), sizeof(double) * 2 * kPointChunk, cudaHostAllocDefault);
+            if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&ps->h_out[k]), sizeof(double) * kPointChunk, cudaHostAllocDefault);
+            if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ps->d_in[k]), sizeof(double) * 2 * kPointChunk);
+            if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ps->d_out[k]), sizeof(double) * kPointChunk);
+        }
+        if (e != cudaSuccess) { release_staging(ps); return fail_cuda("point staging", e); }
+    }
+    g->staging = ps;
+    for (int k = 0; k < 2; ++k) { g->h_in[k] = ps->h_in[k]; g->h_out[k] = ps->h_out[k]; g->d_in[k] = ps->d_in[k]; g->d_out[k] = ps->d_out[k]; }
     return 0;
+}
+
+// Host threads for packing / unpacking point records (memory-bound loops): a few are enough to reach the copy rate.
+int pack_threads(int64_t cnt) {
+    if (cnt < 32768) return 1;
+    const int hw = omp_get_max_threads();
+    return hw < 8 ? (hw < 1 ? 1 : hw) : 8;
 }
 
 }  // namespace
@@ -275,6 +323,9 @@ int auvi_trim(void) {
     for (auto& b : g_cache) { cudaSetDevice(b.device); cudaFree(b.p); }
     g_cache.clear();
     g_cache_held = 0;
+    std::lock_guard<std::mutex> lk2(g_staging_mu);
+    for (PointStaging* ps : g_staging_free) { cudaSetDevice(ps->device); release_staging(ps); }
+    g_staging_free.clear();
     return 0;
 }
 const char* auvi_last_error(void) { return t_error.c_str(); }
@@ -336,9 +387,6 @@ int auvi_grid_destroy(auvi_grid* g) {
     cudaDeviceSynchronize();
     for (auto& kv : g->axes) free_axis(kv.second, g->device);
     for (int k = 0; k < 2; ++k) {
-        if (g->h_in[k]) cudaFreeHost(g->h_in[k]);
-        if (g->h_out[k]) cudaFreeHost(g->h_out[k]);
-        cudaFree(g->d_in[k]); cudaFree(g->d_out[k]);
         cached_free(g->d_rows[k], g->d_rows_bytes, g->device);
         if (g->ev_k0[k]) cudaEventDestroy(g->ev_k0[k]);
         if (g->ev_k1[k]) cudaEventDestroy(g->ev_k1[k]);
@@ -346,6 +394,10 @@ int auvi_grid_destroy(auvi_grid* g) {
         if (g->st[k]) cudaStreamDestroy(g->st[k]);
     }
     cached_free(g->owned, g->owned_bytes, g->device);
+    if (g->staging) {
+        std::lock_guard<std::mutex> lk(g_staging_mu);
+        g_staging_free.push_back(g->staging);
+    }
     delete g;
     return 0;
 }
@@ -385,15 +437,19 @@ int auvi_interp_points(auvi_grid* g, int method, const void* host_pts, int64_t n
     const int64_t sd = stride_bytes / 8, od = out_stride_bytes / 8;
     const double* src = static_cast<const double*>(host_pts);
     double* dst = static_cast<double*>(host_out);
-    const int64_t n_chunks = (n + kPointChunk - 1) / kPointChunk;
+    int64_t chunk = (n + 3) / 4;                                   // ~4 stages for a small batch, 1 Mi points at most
+    chunk = chunk < kPointChunkMin ? kPointChunkMin : (chunk > kPointChunk ? kPointChunk : chunk);
+    const int64_t n_chunks = (n + chunk - 1) / chunk;
     float ms_total = 0.f;
     auto drain = [&](int64_t c) -> int {                         // chunk c: wait, unpack, account
         const int b = static_cast<int>(c & 1);
-        const int64_t lo = c * kPointChunk, cnt = (n - lo < kPointChunk) ? n - lo : kPointChunk;
+        const int64_t lo = c * chunk, cnt = (n - lo < chunk) ? n - lo : chunk;
         AUVI_CUDA(cudaEventSynchronize(g->ev_done[b]));
         const double* r = g->h_out[b];
-        if (od == 1) std::memcpy(dst + lo, r, sizeof(double) * cnt);
-        else for (int64_t k = 0; k < cnt; ++k) dst[(lo + k) * od] = r[k];
+        double* const d0 = dst + lo * od;
+        const int nt = pack_threads(cnt);
+#pragma omp parallel for schedule(static) num_threads(nt) if (nt > 1)
+        for (int64_t k = 0; k < cnt; ++k) d0[k * od] = r[k];
         float ms = 0.f;
         AUVI_CUDA(cudaEventElapsedTime(&ms, g->ev_k0[b], g->ev_k1[b]));
         ms_total += ms;
@@ -401,10 +457,12 @@ int auvi_interp_points(auvi_grid* g, int method, const void* host_pts, int64_t n
     };
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int b = static_cast<int>(c & 1);
-        const int64_t lo = c * kPointChunk, cnt = (n - lo < kPointChunk) ? n - lo : kPointChunk;
+        const int64_t lo = c * chunk, cnt = (n - lo < chunk) ? n - lo : chunk;
         if (c >= 2 && drain(c - 2)) return 2;                     // buffer b is free again after this
         double* pin = g->h_in[b];
         const double* s = src + lo * sd;
+        const int nt = pack_threads(cnt);
+#pragma omp parallel for schedule(static) num_threads(nt) if (nt > 1)
         for (int64_t k = 0; k < cnt; ++k) { pin[2 * k] = s[k * sd]; pin[2 * k + 1] = s[k * sd + 1]; }
         cudaStream_t st = g->st[b];
         AUVI_CUDA(cudaMemcpyAsync(g->d_in[b], pin, sizeof(double) * 2 * cnt, cudaMemcpyHostToDevice, st));
