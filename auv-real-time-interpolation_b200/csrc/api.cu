@@ -170,7 +170,7 @@ int make_streams(auvi_grid* g) {
 
 int check_common(const auvi_grid* g, int method) {
     if (!g) return fail("null grid handle");
-    if (method < AUVI_BILINEAR || method > AUVI_IDW) return fail("unknown interpolation method");
+    if (method < AUVI_BILINEAR || method > AUVI_BILINEAR_SEARCH) return fail("unknown interpolation method");
     return 0;
 }
 

@@ -16,7 +16,7 @@
 
 namespace auvi {
 
-enum Method : int { BILINEAR = 0, CUBIC = 1, KRIGING = 2, NN = 3, IDW = 4 };
+enum Method : int { BILINEAR = 0, CUBIC = 1, KRIGING = 2, NN = 3, IDW = 4, BILINEAR_SEARCH = 5 };
 
 constexpr int kMaxRadius = 10;   // GridH.cpp:275, :339
 constexpr int kMaxCand   = 45;   // 3 + 2*(2*10+1): the most the early-terminating search can hold
@@ -353,6 +353,17 @@ __device__ double interp_exact(const GridView<T>& g, int method, double lon, dou
     if (isnan(x) || isnan(y)) return qnan();
     if (method == BILINEAR) { if (sel) sel->found = -2; return exact_bilinear(g, x, y); }
     if (method == CUBIC) return exact_cubic(g, x, y, sel);
+    if (method == BILINEAR_SEARCH) {
+        // OPT-IN (not a reference method): bilinear wherever the reference's bilinear returns a
+        // number; where it returns NaN (all four corners missing, GridH.cpp:186-198) the 4-nearest mean the bicubic
+        // method falls back to (floor-centred ring search, GridH.cpp:272-318).
+        const double b = exact_bilinear(g, x, y);
+        if (!isnan(b)) { if (sel) sel->found = -2; return b; }
+        Picked p;
+        search_and_pick(g, x, y, static_cast<int>(floor(x)), static_cast<int>(floor(y)), p);
+        if (sel) *sel = p;
+        return p.found < 4 ? mean_found(p) : mean_valid4(p.v[0], p.v[1], p.v[2], p.v[3]);
+    }
     Picked p;
     int ci = round_centre(x, g.n_lon), cj = round_centre(y, g.n_lat);
     search_and_pick(g, x, y, ci, cj, p);

@@ -177,7 +177,7 @@ template <typename T, int METHOD>
 __device__ __forceinline__ T finish_four(const FillParams<T>& p, const T (&v)[4], const double (&d2)[4], const int (&pi)[4],
                                          const int (&pj)[4], int I, int64_t J) {
     if (METHOD == NN) return v[0];
-    if (METHOD == CUBIC) {
+    if (METHOD == CUBIC || METHOD == BILINEAR_SEARCH) {
         // fallbackAverage (GridH.cpp:10-18) of four numbers: ((0 + a) + b + c + d) / 4
         const double sum = dadd(dadd(dadd(dadd(0.0, static_cast<double>(v[0])), static_cast<double>(v[1])),
                                      static_cast<double>(v[2])), static_cast<double>(v[3]));
@@ -340,7 +340,7 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         int c = 0;
         if (I < p.n_out_cols) {
             x = __ldg(p.lon.pos + I);
-            c = (METHOD == CUBIC || METHOD == BILINEAR) ? __ldg(p.lon.base + I) : (isnan(x) ? 0 : round_centre(x, p.g.n_lon));
+            c = (METHOD == CUBIC || METHOD == BILINEAR || METHOD == BILINEAR_SEARCH) ? __ldg(p.lon.base + I) : (isnan(x) ? 0 : round_centre(x, p.g.n_lon));
         }
         s.x[tid] = x; s.cx[tid] = c;
         const double cf = dadd(__int2double_rn(c), 0.5);
@@ -353,7 +353,7 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         int c = 0;
         if (J < p.row_end) {
             y = __ldg(p.lat.pos + J);
-            c = (METHOD == CUBIC || METHOD == BILINEAR) ? __ldg(p.lat.base + J) : (isnan(y) ? 0 : round_centre(y, p.g.n_lat));
+            c = (METHOD == CUBIC || METHOD == BILINEAR || METHOD == BILINEAR_SEARCH) ? __ldg(p.lat.base + J) : (isnan(y) ? 0 : round_centre(y, p.g.n_lat));
         }
         s.y[t] = y; s.cy[t] = c;
         const double cf = dadd(__int2double_rn(c), 0.5);
@@ -409,7 +409,7 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     __syncthreads();
 
     // ---- BILINEAR: no search -- the four corners around the query sit in the tile (GridH.cpp:160-210) -----------------
-    if (METHOD == BILINEAR) {
+    if (METHOD == BILINEAR || METHOD == BILINEAR_SEARCH) {
         const int qn_b = s.qn;
         for (int q = tid; q < qn_b; q += kFThreads) {
             const int k = queue[q];
@@ -432,9 +432,17 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                     result = dadd(dmul(dsub(1.0, wy), lo), dmul(wy, hi));
                 }
             }
-            __stcs(out_tile + lj * p.out_ld + li, static_cast<T>(result));
+            // BILINEAR_SEARCH (opt-in): a query whose four corners are all missing goes on to the ring search
+            if (METHOD == BILINEAR_SEARCH && isnan(result) && !isnan(x) && !isnan(y)) defer[atomicAdd(&s.dn, 1)] = static_cast<uint16_t>(k);
+            else __stcs(out_tile + lj * p.out_ld + li, static_cast<T>(result));
         }
-        return;
+        if (METHOD == BILINEAR) return;
+        __syncthreads();
+        const int left = s.dn;
+        for (int q = tid; q < left; q += kFThreads) queue[q] = defer[q];
+        __syncthreads();
+        if (tid == 0) { s.qn = left; s.dn = 0; }
+        __syncthreads();
     }
 
     auto window = [&](int row, int wi, int sh) -> uint32_t {       // validity of columns ci-10..ci+10 of a tile row
@@ -841,10 +849,10 @@ cudaError_t launch_fill(const GridDesc& d, int method, const AxisTables& lat, co
     if (fill) {
         if (d.dtype == DT_F64) {
             switch (method) { AUVI_CASE(double, BILINEAR, true) AUVI_CASE(double, CUBIC, true) AUVI_CASE(double, KRIGING, true)
-                              AUVI_CASE(double, NN, true) AUVI_CASE(double, IDW, true) }
+                              AUVI_CASE(double, NN, true) AUVI_CASE(double, IDW, true) AUVI_CASE(double, BILINEAR_SEARCH, true) }
         } else {
             switch (method) { AUVI_CASE(float, BILINEAR, true) AUVI_CASE(float, CUBIC, true) AUVI_CASE(float, KRIGING, true)
-                              AUVI_CASE(float, NN, true) AUVI_CASE(float, IDW, true) }
+                              AUVI_CASE(float, NN, true) AUVI_CASE(float, IDW, true) AUVI_CASE(float, BILINEAR_SEARCH, true) }
         }
     } else {                                   // upsampling lattice, the search-based methods (every cell is a query)
         if (d.dtype == DT_F64) {

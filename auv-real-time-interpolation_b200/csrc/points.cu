@@ -68,7 +68,7 @@ cudaError_t launch_points_t(const GridView<T>& g, int method, const double* pts,
     const unsigned blocks = static_cast<unsigned>((n + kPointsBlock - 1) / kPointsBlock);
     switch (method) {
 #define AUVI_CASE(M) case M: points_kernel<T, M><<<blocks, kPointsBlock, 0, st>>>(g, pts, stride_dbl, n, out, sel, found); break;
-        AUVI_CASE(BILINEAR) AUVI_CASE(CUBIC) AUVI_CASE(KRIGING) AUVI_CASE(NN) AUVI_CASE(IDW)
+        AUVI_CASE(BILINEAR) AUVI_CASE(CUBIC) AUVI_CASE(KRIGING) AUVI_CASE(NN) AUVI_CASE(IDW) AUVI_CASE(BILINEAR_SEARCH)
 #undef AUVI_CASE
         default: return cudaErrorInvalidValue;
     }

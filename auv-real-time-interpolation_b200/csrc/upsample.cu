@@ -462,7 +462,7 @@ static cudaError_t launch_lattice_t(const GridDesc& d, int method, const AxisTab
         return fill ? launch_exact<T, M, true>(d, lat, lon, row_begin, row_end, out, out_ld, sel, st, info)  \
                     : launch_exact<T, M, false>(d, lat, lon, row_begin, row_end, out, out_ld, sel, st, info);
     switch (method) {
-        AUVI_CASE(BILINEAR) AUVI_CASE(CUBIC) AUVI_CASE(KRIGING) AUVI_CASE(NN) AUVI_CASE(IDW)
+        AUVI_CASE(BILINEAR) AUVI_CASE(CUBIC) AUVI_CASE(KRIGING) AUVI_CASE(NN) AUVI_CASE(IDW) AUVI_CASE(BILINEAR_SEARCH)
         default: return cudaErrorInvalidValue;
     }
 #undef AUVI_CASE

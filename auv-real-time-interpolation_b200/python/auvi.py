@@ -21,8 +21,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB_PATH = os.path.join(PKG, "lib", "libauvi.so")
 
-BILINEAR, CUBIC, KRIGING, NN, IDW = 0, 1, 2, 3, 4
-METHOD_NAMES = {BILINEAR: "bilinear", CUBIC: "cubic", KRIGING: "kriging", NN: "nn", IDW: "idw"}
+BILINEAR, CUBIC, KRIGING, NN, IDW, BILINEAR_SEARCH = 0, 1, 2, 3, 4, 5
+METHOD_NAMES = {BILINEAR: "bilinear", CUBIC: "cubic", KRIGING: "kriging", NN: "nn", IDW: "idw",
+                BILINEAR_SEARCH: "bilinear_search"}
 F64, F32 = 0, 1
 AXIS_EXPANDED, AXIS_NODES = 0, 1
 

@@ -606,7 +606,7 @@ def extra_mariana(torch, auvi, local):
     d_truth = torch.from_numpy(case["truth"]).cuda()
     res = {}
     for name, meth in (("bilinear", auvi.BILINEAR), ("cubic", auvi.CUBIC), ("kriging", auvi.KRIGING),
-                       ("nn", auvi.NN), ("idw", auvi.IDW)):
+                       ("nn", auvi.NN), ("idw", auvi.IDW), ("bilinear_search(opt-in)", auvi.BILINEAR_SEARCH)):
         g.interp_points(meth, case["pts"])
         t0 = time.perf_counter()
         for _ in range(5):

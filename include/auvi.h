@@ -23,7 +23,10 @@ typedef struct auvi_grid auvi_grid;   /* opaque: a depth grid (or a row slab of 
 
 /* Interpolation methods.  0-2 are the reference's three (include/GridD.h:69,77,85);
  * 3-4 are extensions defined on the reference's own neighbour search. */
-enum { AUVI_BILINEAR = 0, AUVI_CUBIC = 1, AUVI_KRIGING = 2, AUVI_NN = 3, AUVI_IDW = 4 };
+enum { AUVI_BILINEAR = 0, AUVI_CUBIC = 1, AUVI_KRIGING = 2, AUVI_NN = 3, AUVI_IDW = 4,
+       /* opt-in, changes results: bilinear, and where the reference's bilinear returns NaN (all four
+        * corners missing, GridH.cpp:186-198) the ring-search 4-nearest mean of the bicubic fallback (GridH.cpp:272-318) */
+       AUVI_BILINEAR_SEARCH = 5 };
 /* Storage type of the depth grid and of lattice outputs. */
 enum { AUVI_F64 = 0, AUVI_F32 = 1 };
 /* How a lattice axis maps an output index to a coordinate:

@@ -607,3 +607,34 @@ def test_config4_full_size_strips_against_exact_path(auvi, torch):
                 err = (got[ok].double() - ref[ok].double()).abs() - 1e-5 * ref[ok].double().abs()
                 assert float(err.max()) <= 1e-3
     g.close()
+
+
+# ---- opt-in method: bilinear with the bicubic method's search fallback --------------------------------
+def _bilinear_search_expected(orc, pts):
+    """AUVI_BILINEAR_SEARCH composed from two reference methods: bilinear, and -- exactly where that is NaN for an in-bounds
+    query, i.e. all four corners missing, which puts NaN into the bicubic 4x4 stencil too -- the bicubic method's
+    floor-centred 4-nearest mean."""
+    b = orc.batch(ob.BILINEAR, pts)
+    c = orc.batch(ob.CUBIC, pts)
+    return np.where(np.isnan(b), c, b)
+
+
+@pytest.mark.parametrize("name,frac", [("mid_atlantic", 0.5), ("mid_atlantic", 0.9), ("mariana", 0.5)])
+def test_bilinear_search_opt_in(auvi, torch, name, frac):
+    case = ob.masked_case(name, frac)
+    orc = ob.Oracle(case["z"], *case["bounds"])
+    g = auvi.Grid(case["z"], *case["bounds"])
+    want = _bilinear_search_expected(orc, case["pts"])
+    assert np.isnan(orc.batch(ob.BILINEAR, case["pts"])).sum() > 0 and not np.isnan(want).any()
+    # point list (exact path), full-grid fill (tiled kernel), and a 2x lattice with holes (exact path)
+    assert bits_equal(g.interp_points(auvi.BILINEAR_SEARCH, case["pts"]), want)
+    filled = g.lattice(auvi.BILINEAR_SEARCH, auvi.AXIS_NODES, 1, 1, fill=1)
+    assert bits_equal(filled[case["rows"], case["cols"]], want)
+    keep = ~np.isnan(case["z"])
+    assert bits_equal(filled[keep], case["z"][keep])
+    m = case["meta"]
+    q, nn_lat, nn_lon = ob.lattice_queries(m["n_lat"], m["n_lon"], *case["bounds"])
+    sub = slice(0, 40 * nn_lon)                                       # the first 40 lattice rows
+    got = g.lattice(auvi.BILINEAR_SEARCH, auvi.AXIS_EXPANDED, 2, 2, row_begin=0, row_end=40)
+    assert bits_equal(got.ravel(), _bilinear_search_expected(orc, q[sub]))
+    g.close()
