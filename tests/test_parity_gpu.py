@@ -638,3 +638,39 @@ def test_bilinear_search_opt_in(auvi, torch, name, frac):
     got = g.lattice(auvi.BILINEAR_SEARCH, auvi.AXIS_EXPANDED, 2, 2, row_begin=0, row_end=40)
     assert bits_equal(got.ravel(), _bilinear_search_expected(orc, q[sub]))
     g.close()
+
+
+@pytest.mark.parametrize("shape", [(2, 2), (3, 5), (7, 130), (17, 70), (65, 33), (100, 3), (33, 257)])
+def test_tiny_and_ragged_grids_every_path(auvi, shape):
+    """Grids smaller than a tile (down to 2 x 2, the smallest a GridD can hold), narrower than the TMA box, with row
+    pitches that need padding: gap fill, 2x / 3x lattices and point lists of every method against the oracle."""
+    n_lat, n_lon = shape
+    rng = np.random.RandomState(n_lat * 1000 + n_lon)
+    z = np.round(rng.uniform(-6000.0, -100.0, size=shape))
+    for frac in (0.0, 0.4, 0.85):
+        zm = z.copy()
+        zm[rng.rand(*shape) < frac] = np.nan
+        if frac > 0 and not np.isnan(zm).any():
+            zm[0, 0] = np.nan
+        bounds = (10.0, 10.0 + 0.01 * (n_lon - 1), -5.0, -5.0 + 0.013 * (n_lat - 1))
+        orc = ob.Oracle(zm, *bounds)
+        g = auvi.Grid(zm, *bounds)
+        meta = dict(n_lat=n_lat, n_lon=n_lon, min_lon=bounds[0], max_lon=bounds[1], min_lat=bounds[2], max_lat=bounds[3])
+        rows, cols = np.nonzero(np.isnan(zm))
+        node_pts = ob.node_queries(rows, cols, meta) if rows.size else np.zeros((0, 3))
+        for meth in METHODS:
+            tight = meth in (ob.BILINEAR, ob.CUBIC, ob.NN)
+            if rows.size:
+                filled = g.lattice(meth, auvi.AXIS_NODES, 1, 1, fill=1)
+                want = orc.batch(meth, node_pts)
+                got = filled[rows, cols]
+                if tight: assert bits_equal(got, want), (shape, frac, ob.METHOD_NAMES[meth])
+                else: _close(got, want, atol=TIGHT if meth == ob.KRIGING else 1e-3, rtol=0 if meth == ob.KRIGING else 1e-5)
+                assert bits_equal(filled[~np.isnan(zm)], zm[~np.isnan(zm)])
+            for f in (2, 3):
+                q, nn_lat, nn_lon = ob.lattice_queries(n_lat, n_lon, *bounds, f_lat=f, f_lon=f)
+                got = g.lattice(meth, auvi.AXIS_EXPANDED, f, f).ravel()
+                want = orc.batch(meth, q)
+                if tight: assert bits_equal(got, want), (shape, frac, f, ob.METHOD_NAMES[meth])
+                else: _close(got, want, atol=TIGHT if meth == ob.KRIGING else 1e-3, rtol=0 if meth == ob.KRIGING else 1e-5)
+        g.close()
