@@ -121,6 +121,7 @@ void cached_free(void* p, size_t bytes, int device) {
 constexpr int64_t kPointChunk = 1 << 20;            // most queries per pipeline stage (16 MiB in, 8 MiB out)
 constexpr int64_t kPointChunkMin = 1 << 16;         // smaller batches are cut into ~4 stages so that packing overlaps the copies
 constexpr int64_t kLatticeChunkBytes = 256ll << 20; // device staging per pipeline stage, lattice host form
+constexpr int64_t kBounceBytes = 64ll << 20;        // ... when the destination is pageable: stage size of the pinned bounce ring
 
 }  // namespace
 
@@ -299,6 +300,35 @@ int ensure_point_staging(auvi_grid* g) {
     return 0;
 }
 
+// Pinned bounce ring of the lattice host form (pageable destinations), one per process, grown on demand.
+std::mutex g_bounce_mu;
+char* g_bounce[2] = {nullptr, nullptr};
+size_t g_bounce_bytes = 0;
+bool g_bounce_busy = false;
+
+int acquire_bounce(size_t need, char* (&out)[2]) {
+    std::lock_guard<std::mutex> lk(g_bounce_mu);
+    if (g_bounce_busy) {                                           // another thread is in a lattice call: private ring
+        for (int k = 0; k < 2; ++k) AUVI_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&out[k]), need, cudaHostAllocDefault));
+        return 0;
+    }
+    if (need > g_bounce_bytes) {
+        for (int k = 0; k < 2; ++k) { if (g_bounce[k]) cudaFreeHost(g_bounce[k]); g_bounce[k] = nullptr; }
+        g_bounce_bytes = 0;
+        for (int k = 0; k < 2; ++k) AUVI_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_bounce[k]), need, cudaHostAllocDefault));
+        g_bounce_bytes = need;
+    }
+    out[0] = g_bounce[0]; out[1] = g_bounce[1];
+    g_bounce_busy = true;
+    return 0;
+}
+
+void release_bounce(char* (&ring)[2], size_t) {
+    std::lock_guard<std::mutex> lk(g_bounce_mu);
+    if (ring[0] == g_bounce[0]) { g_bounce_busy = false; return; }
+    for (int k = 0; k < 2; ++k) if (ring[k]) cudaFreeHost(ring[k]);
+}
+
 // Host threads for packing / unpacking point records (memory-bound loops): a few are enough to reach the copy rate.
 int pack_threads(int64_t cnt) {
     if (cnt < 32768) return 1;
@@ -326,6 +356,13 @@ int auvi_trim(void) {
     std::lock_guard<std::mutex> lk2(g_staging_mu);
     for (PointStaging* ps : g_staging_free) { cudaSetDevice(ps->device); release_staging(ps); }
     g_staging_free.clear();
+    {
+        std::lock_guard<std::mutex> lk3(g_bounce_mu);
+        if (!g_bounce_busy) {
+            for (int k = 0; k < 2; ++k) { if (g_bounce[k]) cudaFreeHost(g_bounce[k]); g_bounce[k] = nullptr; }
+            g_bounce_bytes = 0;
+        }
+    }
     return 0;
 }
 const char* auvi_last_error(void) { return t_error.c_str(); }
@@ -528,11 +565,19 @@ int auvi_lattice(auvi_grid* g, int method, int axis_kind, int f_lat, int f_lon, 
     AUVI_CUDA(cudaSetDevice(g->device));
     const size_t es = g->d.dtype == AUVI_F64 ? 8 : 4;
     const int64_t row_bytes = cols * static_cast<int64_t>(es);
-    static const int64_t chunk_bytes = [] {                           // tuning knob, MiB
+    // Pageable destination (a std::vector, a numpy array): a device->host copy into it is staged by the driver at
+    // 16-20 GB/s.  Bounce through our own pinned ring instead and move the rows out with a few host threads while the
+    // next chunk is on the wire.  A pinned / registered destination is written directly.
+    cudaPointerAttributes attr;
+    bool pageable = true;
+    if (cudaPointerGetAttributes(&attr, host_out) == cudaSuccess) pageable = attr.type == cudaMemoryTypeUnregistered;
+    else cudaGetLastError();
+    static const int64_t chunk_knob = [] {                            // tuning knob, MiB
         const char* e = getenv("AUVI_LATTICE_CHUNK_MB");
         const long v = e ? atol(e) : 0;
-        return v > 0 ? static_cast<int64_t>(v) << 20 : kLatticeChunkBytes;
+        return v > 0 ? static_cast<int64_t>(v) << 20 : 0ll;
     }();
+    const int64_t chunk_bytes = chunk_knob ? chunk_knob : (pageable ? kBounceBytes : kLatticeChunkBytes);
     int64_t chunk_rows = chunk_bytes / row_bytes;
     if (chunk_rows < 1) chunk_rows = 1;
     if (chunk_rows > row_end - row_begin) chunk_rows = row_end - row_begin;
@@ -543,35 +588,50 @@ int auvi_lattice(auvi_grid* g, int method, int axis_kind, int f_lat, int f_lon, 
         for (int k = 0; k < 2; ++k) AUVI_CUDA(cached_malloc(&g->d_rows[k], need, g->device));
         g->d_rows_bytes = need;
     }
+    char* bounce[2] = {nullptr, nullptr};
+    if (pageable) {
+        if (acquire_bounce(need, bounce)) return 2;
+    }
     float ms_total = 0.f;
     int64_t c = 0;
-    for (int64_t r = row_begin; r < row_end; r += chunk_rows, ++c) {
-        const int b = static_cast<int>(c & 1);
-        const int64_t r_hi = (r + chunk_rows < row_end) ? r + chunk_rows : row_end;
-        cudaStream_t st = g->st[b];
-        if (c >= 2) {                                             // staging buffer b: previous copy drained?
-            AUVI_CUDA(cudaEventSynchronize(g->ev_done[b]));
-            float ms = 0.f;
-            AUVI_CUDA(cudaEventElapsedTime(&ms, g->ev_k0[b], g->ev_k1[b]));
-            ms_total += ms;
-        }
-        AUVI_CUDA(cudaEventRecord(g->ev_k0[b], st));
-        if (auvi_lattice_device(g, method, axis_kind, f_lat, f_lon, fill, r, r_hi, g->d_rows[b], cols, nullptr, st))
-            return 2;
-        AUVI_CUDA(cudaEventRecord(g->ev_k1[b], st));
-        AUVI_CUDA(cudaMemcpyAsync(static_cast<char*>(host_out) + (r - row_begin) * row_bytes, g->d_rows[b],
-                                  static_cast<size_t>(r_hi - r) * row_bytes, cudaMemcpyDeviceToHost, st));
-        AUVI_CUDA(cudaEventRecord(g->ev_done[b], st));
-    }
-    for (int64_t k = (c >= 2 ? c - 2 : 0); k < c; ++k) {
-        const int b = static_cast<int>(k & 1);
+    int64_t lo_of[2] = {0, 0}, hi_of[2] = {0, 0};
+    auto drain = [&](int b) -> int {                               // chunk in staging slot b: wait, move out, account
         AUVI_CUDA(cudaEventSynchronize(g->ev_done[b]));
+        if (pageable) {
+            char* const dst = static_cast<char*>(host_out) + (lo_of[b] - row_begin) * row_bytes;
+            const int64_t bytes = (hi_of[b] - lo_of[b]) * row_bytes;
+            const int nt = pack_threads(bytes / 16);
+            const int64_t piece = (bytes / nt + 4095) & ~4095ll;
+#pragma omp parallel for schedule(static) num_threads(nt) if (nt > 1)
+            for (int t = 0; t < nt; ++t) {
+                const int64_t at = t * piece, len = at + piece <= bytes ? piece : bytes - at;
+                if (len > 0) std::memcpy(dst + at, bounce[b] + at, static_cast<size_t>(len));
+            }
+        }
         float ms = 0.f;
         AUVI_CUDA(cudaEventElapsedTime(&ms, g->ev_k0[b], g->ev_k1[b]));
         ms_total += ms;
+        return 0;
+    };
+    int rc = 0;
+    for (int64_t r = row_begin; r < row_end && !rc; r += chunk_rows, ++c) {
+        const int b = static_cast<int>(c & 1);
+        const int64_t r_hi = (r + chunk_rows < row_end) ? r + chunk_rows : row_end;
+        cudaStream_t st = g->st[b];
+        if (c >= 2 && (rc = drain(b))) break;                     // staging slot b is free again after this
+        lo_of[b] = r; hi_of[b] = r_hi;
+        cudaError_t e = cudaEventRecord(g->ev_k0[b], st);
+        if (e == cudaSuccess && auvi_lattice_device(g, method, axis_kind, f_lat, f_lon, fill, r, r_hi, g->d_rows[b], cols, nullptr, st)) { rc = 2; break; }
+        if (e == cudaSuccess) e = cudaEventRecord(g->ev_k1[b], st);
+        char* const target = pageable ? bounce[b] : static_cast<char*>(host_out) + (r - row_begin) * row_bytes;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(target, g->d_rows[b], static_cast<size_t>(r_hi - r) * row_bytes, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaEventRecord(g->ev_done[b], st);
+        if (e != cudaSuccess) { rc = fail_cuda("lattice copy", e); break; }
     }
+    for (int64_t k = (c >= 2 ? c - 2 : 0); k < c && !rc; ++k) rc = drain(static_cast<int>(k & 1));
+    if (pageable) { cudaDeviceSynchronize(); release_bounce(bounce, need); }
     g->last_ms = ms_total;
-    return 0;
+    return rc;
 }
 
 // ---- metrics ---------------------------------------------------------------------------------------

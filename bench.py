@@ -370,6 +370,31 @@ def main():
             del probe_d, probe_h
         except Exception:
             pass
+        # the same call with a PAGEABLE destination (what a std::vector / numpy caller has), on a bounded row range
+        try:
+            p_rows = min(e2e_rows, 8192)
+            pageable = np.zeros((p_rows, out_cols), dtype=np.float32)             # touched, like a value-initialised vector
+            h = C.c_void_p()
+            if world == 1:
+                assert lib.auvi_grid_create(h_z.data_ptr(), auvi.F32, n_lat_global, n_lon, *bounds, local, C.byref(h)) == 0
+                keep = None
+            else:
+                keep = h_z.to(dev)
+                assert lib.auvi_grid_adopt(keep.data_ptr(), auvi.F32, n_lat_global, n_lon, n_lon, in_lo, in_hi - in_lo, *bounds, local, C.byref(h)) == 0
+            pp = pageable.ctypes.data
+            assert lib.auvi_lattice(h, auvi.CUBIC, auvi.AXIS_EXPANDED, FACTOR, FACTOR, 0, row_lo, row_lo + p_rows, pp) == 0
+            t0 = time.perf_counter()
+            for _ in range(2):
+                assert lib.auvi_lattice(h, auvi.CUBIC, auvi.AXIS_EXPANDED, FACTOR, FACTOR, 0, row_lo, row_lo + p_rows, pp) == 0
+            dtp = (time.perf_counter() - t0) / 2
+            lib.auvi_grid_destroy(h)
+            del keep
+            e2e["pageable_host"] = {"rows": p_rows, "ms": dtp * 1e3, "GBps_d2h": p_rows * out_cols * 4 / dtp / 1e9,
+                                    "Mcells_per_s_this_rank": p_rows * out_cols / dtp / 1e6,
+                                    "equals_pinned_result": bool(np.array_equal(pageable[:64], h_out[:64].numpy()))}
+            del pageable
+        except Exception as exc:
+            e2e["pageable_host"] = {"unavailable": repr(exc)[:200]}
         # spot check: the host result equals the device-resident result
         chk = slice(e2e_rows // 2, e2e_rows // 2 + 8)
         assert torch.equal(h_out[chk], out[chk, :out_cols].cpu())
