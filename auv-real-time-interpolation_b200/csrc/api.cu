@@ -600,7 +600,8 @@ int auvi_lattice(auvi_grid* g, int method, int axis_kind, int f_lat, int f_lon, 
         if (pageable) {
             char* const dst = static_cast<char*>(host_out) + (lo_of[b] - row_begin) * row_bytes;
             const int64_t bytes = (hi_of[b] - lo_of[b]) * row_bytes;
-            const int nt = pack_threads(bytes / 16);
+            const int hw = omp_get_max_threads();
+            const int nt = bytes < (1 << 20) ? 1 : (hw < 16 ? (hw < 1 ? 1 : hw) : 16);   // a plain copy: bandwidth-bound, more threads help
             const int64_t piece = (bytes / nt + 4095) & ~4095ll;
 #pragma omp parallel for schedule(static) num_threads(nt) if (nt > 1)
             for (int t = 0; t < nt; ++t) {
