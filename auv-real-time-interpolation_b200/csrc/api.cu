@@ -329,6 +329,52 @@ void release_bounce(char* (&ring)[2], size_t) {
     for (int k = 0; k < 2; ++k) if (ring[k]) cudaFreeHost(ring[k]);
 }
 
+// Dense host rows -> pitched device rows.  A pinned source goes in one 2-D copy; a pageable one (a std::vector) is
+// copied by host threads into the pinned ring stage by stage while the previous stage is on the wire, instead of the
+// driver's own staged copy.
+cudaError_t upload_rows(void* dev, size_t dev_pitch, const void* host, size_t row_bytes, int64_t n_rows) {
+    cudaPointerAttributes attr;
+    bool pageable = true;
+    if (cudaPointerGetAttributes(&attr, host) == cudaSuccess) pageable = attr.type == cudaMemoryTypeUnregistered;
+    else cudaGetLastError();
+    const size_t total = row_bytes * static_cast<size_t>(n_rows);
+    if (!pageable || total < (8u << 20))
+        return cudaMemcpy2D(dev, dev_pitch, host, row_bytes, row_bytes, static_cast<size_t>(n_rows), cudaMemcpyHostToDevice);
+    int64_t stage_rows = kBounceBytes / static_cast<int64_t>(row_bytes);
+    if (stage_rows < 1) stage_rows = 1;
+    const size_t need = static_cast<size_t>(stage_rows) * row_bytes;
+    char* ring[2] = {nullptr, nullptr};
+    if (acquire_bounce(need, ring)) return cudaErrorMemoryAllocation;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+    const int hw = omp_get_max_threads();
+    const int nt = hw < 16 ? (hw < 1 ? 1 : hw) : 16;
+    int64_t c = 0;
+    for (int64_t r = 0; r < n_rows && e == cudaSuccess; r += stage_rows, ++c) {
+        const int b = static_cast<int>(c & 1);
+        const int64_t cnt = r + stage_rows < n_rows ? stage_rows : n_rows - r;
+        if (c >= 2) e = cudaEventSynchronize(ev[b]);
+        if (e != cudaSuccess) break;
+        const char* src = static_cast<const char*>(host) + static_cast<size_t>(r) * row_bytes;
+        const int64_t bytes = cnt * static_cast<int64_t>(row_bytes), piece = (bytes / nt + 4095) & ~4095ll;
+#pragma omp parallel for schedule(static) num_threads(nt)
+        for (int t = 0; t < nt; ++t) {
+            const int64_t at = t * piece, len = at + piece <= bytes ? piece : bytes - at;
+            if (len > 0) std::memcpy(ring[b] + at, src + at, static_cast<size_t>(len));
+        }
+        e = cudaMemcpy2DAsync(static_cast<char*>(dev) + static_cast<size_t>(r) * dev_pitch, dev_pitch, ring[b], row_bytes, row_bytes,
+                              static_cast<size_t>(cnt), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[b], st);
+    }
+    if (st) { const cudaError_t e2 = cudaStreamSynchronize(st); if (e == cudaSuccess) e = e2; }
+    for (int k = 0; k < 2; ++k) if (ev[k]) cudaEventDestroy(ev[k]);
+    if (st) cudaStreamDestroy(st);
+    release_bounce(ring, need);
+    return e;
+}
+
 // Host threads for packing / unpacking point records (memory-bound loops): a few are enough to reach the copy rate.
 int pack_threads(int64_t cnt) {
     if (cnt < 32768) return 1;
@@ -387,8 +433,7 @@ int auvi_grid_create(const void* host_rowmajor, int dtype, int64_t n_lat, int64_
     cudaError_t e = cudaSetDevice(device);
     g->owned_bytes = static_cast<size_t>(ld) * n_lat * es;
     if (e == cudaSuccess) e = cached_malloc(&g->owned, g->owned_bytes, device);
-    if (e == cudaSuccess)
-        e = cudaMemcpy2D(g->owned, ld * es, host_rowmajor, n_lon * es, n_lon * es, n_lat, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = upload_rows(g->owned, ld * es, host_rowmajor, n_lon * es, n_lat);
     if (e != cudaSuccess) { cudaFree(g->owned); delete g; return fail_cuda("grid upload", e); }
     g->d.z = g->owned; g->d.ld = ld; g->d.row0 = 0; g->d.rows = g->d.n_lat;
     if (make_streams(g)) { auvi_grid_destroy(g); return 2; }
