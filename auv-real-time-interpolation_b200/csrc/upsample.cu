@@ -55,7 +55,10 @@ struct TileParams {
     T* out;
     int64_t out_ld;
     int tj;                        // output rows per CTA
-    int bw, bh;                    // shared-memory input box (elements)
+    int bw, bh;                    // shared-memory input box (elements), per column slab
+    int box_stride;                // elements between the boxes of consecutive slabs (a multiple of 128 bytes: TMA destination)
+    int slabs;                     // 1, 2 or 4: the tile's column threads are split into slabs, each with its own input box
+                                   // (incl. its own stencil halo), when one box would exceed the 256-element TMA limit
     int use_tma;
     int vec_ok;                    // out and out_ld are 16-byte aligned: vector stores allowed
 };
@@ -117,23 +120,33 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     // global column of tile column 0, rounded down to a 16-byte boundary: with no swizzle/interleave
     // the TMA unit faults ("illegal instruction") on a box whose first element is not 16-byte aligned
     // in global memory (measured on B200: profiles/r01_tma_alignment_probe.txt)
-    const int c0 = (__ldg(p.lon.base + I0) - LO) & ~(COLS - 1);
     const int r0 = __ldg(p.lat.base + J0) - LO;                    // global row of tile row 0
     const int bw = p.bw, bh = p.bh;
+    // column slabs: slab s serves column threads [s*kColThreads/S, (s+1)*kColThreads/S) from its own box
+    const int S = p.slabs, slab_cols = kTileCols / S, box_elems = bw * bh, box_stride = p.box_stride;
+    auto slab_c0 = [&](int sl) -> int {                           // global column of box column 0 of slab sl
+        const int Is = I0 + sl * slab_cols;
+        return (__ldg(p.lon.base + (Is < W ? Is : W - 1)) - LO) & ~(COLS - 1);
+    };
 
     // ---- stage the input box -------------------------------------------------------------------
     if (p.use_tma) {
         if (tid == 0) { prefetch_tmap(&tmap); mbar_init(&bar, 1); }
         __syncthreads();
         if (tid == 0) {
-            mbar_expect_tx(&bar, static_cast<uint32_t>(bw * bh * sizeof(T)));
-            tma_load_2d(tile, &tmap, c0, r0 - p.g.row0, &bar);
+            int live = 0;
+            for (int sl = 0; sl < S; ++sl) live += (I0 + sl * slab_cols < W);
+            mbar_expect_tx(&bar, static_cast<uint32_t>(live * box_elems * sizeof(T)));
+            for (int sl = 0; sl < live; ++sl) tma_load_2d(tile + sl * box_stride, &tmap, slab_c0(sl), r0 - p.g.row0, &bar);
         }
     } else {
-        for (int k = tid; k < bw * bh; k += kTileThreads) {        // coalesced, clamp-to-edge
-            int lr = k / bw, lc = k - lr * bw;
-            int gr = clampi(r0 + lr, 0, p.g.n_lat - 1), gc = clampi(c0 + lc, 0, p.g.n_lon - 1);
-            tile[k] = __ldg(p.g.z + static_cast<int64_t>(gr - p.g.row0) * p.g.ld + gc);
+        for (int sl = 0; sl < S && I0 + sl * slab_cols < W; ++sl) {
+            const int c0 = slab_c0(sl);
+            for (int k = tid; k < box_elems; k += kTileThreads) {  // coalesced, clamp-to-edge
+                int lr = k / bw, lc = k - lr * bw;
+                int gr = clampi(r0 + lr, 0, p.g.n_lat - 1), gc = clampi(c0 + lc, 0, p.g.n_lon - 1);
+                tile[sl * box_stride + k] = __ldg(p.g.z + static_cast<int64_t>(gr - p.g.row0) * p.g.ld + gc);
+            }
         }
     }
 
@@ -154,6 +167,9 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     }
     const int ct = tid % kColThreads, rg = tid / kColThreads;
     const int Ic = I0 + ct * COLS;                                 // first of this thread's columns
+    const int my_slab = ct / (kColThreads / S);
+    const int c0 = slab_c0(my_slab);                               // this thread's box
+    const T* const my_tile = tile + my_slab * box_stride;
     int ox[COLS];
     double txd[COLS];
     float wx[kF64 ? 1 : COLS][4];
@@ -175,15 +191,18 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
         mbar_wait(&bar, 0);
         // The reference clamps stencil indices to the grid edge (GridH.cpp:242-247, :172-173); TMA
         // zero-fills instead, so border tiles copy the edge row/column into their out-of-grid halo.
-        const bool border = c0 < 0 || c0 + bw > p.g.n_lon || r0 < 0 || r0 + bh > p.g.n_lat;
-        if (border) {
-            for (int k = tid; k < bw * bh; k += kTileThreads) {
+        for (int sl = 0; sl < S && I0 + sl * slab_cols < W; ++sl) {
+            const int b0 = slab_c0(sl);
+            const bool border = b0 < 0 || b0 + bw > p.g.n_lon || r0 < 0 || r0 + bh > p.g.n_lat;
+            if (!border) continue;
+            T* const box = tile + sl * box_stride;
+            for (int k = tid; k < box_elems; k += kTileThreads) {
                 int lr = k / bw, lc = k - lr * bw;
-                int gr = r0 + lr, gc = c0 + lc;
+                int gr = r0 + lr, gc = b0 + lc;
                 int cr = clampi(gr, 0, p.g.n_lat - 1), cc = clampi(gc, 0, p.g.n_lon - 1);
                 if (cr != gr || cc != gc) {
-                    int sr = cr - r0, sc = cc - c0;                // in-grid source, never rewritten
-                    if (sr >= 0 && sr < bh && sc >= 0 && sc < bw) tile[k] = tile[sr * bw + sc];
+                    int sr = cr - r0, sc = cc - b0;                // in-grid source, never rewritten
+                    if (sr >= 0 && sr < bh && sc >= 0 && sc < bw) box[k] = box[sr * bw + sc];
                 }
             }
         }
@@ -253,7 +272,7 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     T h[TAPS][COLS];
     int jr = jr_begin;
     int top = s_top[jr];                                           // window = tile rows [top, top+TAPS)
-    const T* next_row = tile + top * bw;
+    const T* next_row = my_tile + top * bw;
 #pragma unroll
     for (int k = 0; k < TAPS; ++k, next_row += bw) hrow(next_row, h[k]);
 #pragma unroll 1
@@ -383,10 +402,16 @@ static cudaError_t launch_tiled(const GridDesc& d, const AxisTables& lat, const 
     const int align = static_cast<int>(16 / es);
     int tj = kTileRowsMax;
     const int tile_cols = kColThreads * align;
+    int slabs = 1;
     int bw = max_span(lon.h_base, 0, lon.n, tile_cols, taps, lo, align);
     bw = (bw + align - 1) / align * align;
+    while (bw > 256 && slabs < 4) {                               // a TMA box holds at most 256 elements per dimension
+        slabs *= 2;
+        bw = max_span(lon.h_base, 0, lon.n, tile_cols / slabs, taps, lo, align);
+        bw = (bw + align - 1) / align * align;
+    }
     int bh = max_span(lat.h_base, row_begin, row_end, tj, taps, lo, 1);
-    while (static_cast<size_t>(bw) * bh * es > 96 * 1024 && tj > 8) {       // keep >=2 CTAs/SM of smem
+    while (static_cast<size_t>(slabs) * bw * bh * es > 96 * 1024 && tj > 8) {   // keep >=2 CTAs/SM of smem
         tj /= 2;
         bh = max_span(lat.h_base, row_begin, row_end, tj, taps, lo, 1);
     }
@@ -404,7 +429,8 @@ static cudaError_t launch_tiled(const GridDesc& d, const AxisTables& lat, const 
     p.lon = AxisDev{lon.coord, lon.pos, lon.base, lon.n};
     p.row_begin = row_begin; p.row_end = row_end;
     p.out = static_cast<T*>(out); p.out_ld = out_ld;
-    p.tj = tj; p.bw = bw; p.bh = bh;
+    p.tj = tj; p.bw = bw; p.bh = bh; p.slabs = slabs;
+    p.box_stride = static_cast<int>((static_cast<size_t>(bw) * bh * es + 127) / 128 * 128 / es);
     p.vec_ok = (reinterpret_cast<uintptr_t>(out) % 16 == 0 && (out_ld * es) % 16 == 0) ? 1 : 0;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
@@ -413,7 +439,7 @@ static cudaError_t launch_tiled(const GridDesc& d, const AxisTables& lat, const 
     // grid are patched to the clamped edge row inside the kernel.
     p.use_tma = make_grid_tensor_map(d, bw, bh, &tmap) ? 1 : 0;
 
-    const size_t smem = static_cast<size_t>(bw) * bh * es;
+    const size_t smem = static_cast<size_t>(slabs) * p.box_stride * es;
     auto kern = upsample_tiled_kernel<T, METHOD>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

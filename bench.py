@@ -406,6 +406,17 @@ def main():
         ms_b, _ = timed(lambda: step(auvi.BILINEAR), max(3, args.steps // 2), 2)
         extra["bilinear_4x_upsample_f32"] = {"Mcells_per_s": cells_total / (ms_b * 1e-3) / 1e6, "ms": ms_b,
                                              "hbm_frac": ALGO_BYTES_PER_CELL * cells_rank / (ms_b * 1e-3) / 1e9 / peak}
+        # latitude-only variant: 4x more rows, the same columns -> 4 + 4/4 = 5 B per output cell
+        lat_rows = my_rows
+        out_lat = out.view(-1)[: lat_rows * n_lon].view(lat_rows, n_lon)
+
+        def step_lat():
+            g.lattice_device(auvi.CUBIC, auvi.AXIS_EXPANDED, FACTOR, 1, 0, row_lo, row_hi, out_lat.data_ptr(), n_lon, None, stream)
+
+        ms_l, _ = timed(step_lat, max(3, args.steps // 2), 2)
+        extra["bicubic_4x_latitude_only_f32"] = {"Mcells_per_s": out_rows_global * n_lon / (ms_l * 1e-3) / 1e6, "ms": ms_l,
+                                                 "out_cells_per_gpu": lat_rows * n_lon,
+                                                 "hbm_frac": 5.0 * lat_rows * n_lon / (ms_l * 1e-3) / 1e9 / peak}
         if rank == 0:
             extra.update(extra_gap_fill(torch, auvi, dev, stream, peak))
             extra.update(extra_mariana(torch, auvi, local))
