@@ -1,31 +1,37 @@
-// fill.cu -- full-grid gap fill: every NaN cell of the grid gets METHOD(query at its own node), valid
-// cells pass through.  This is the structured form of the reference's Grid-B procedure
-// (test_gebco.cpp:150-196: one query per removed cell, built by gridIndexToGeo :72-81, evaluated by
-// GridH::batch{Cubic,OrdinaryKriging}Interpolate, GridH.cpp:223-420) and of BASELINE config 4
-// (IDW / nearest-neighbour on a 70 % masked grid).  Methods: BILINEAR (four corners, NaN-corner mean:
-// no search), CUBIC (always the ring-search 4-nearest mean here: a masked cell is inside its own 4x4
-// stencil), KRIGING, NN, IDW.
+// fill.cu -- the tiled ring-search kernel.
 //
-// Design (one CTA = 256 threads = one 64 x 32 tile of cells):
-//   1. The tile + a 12-cell halo (88 x 56 cells: search radius 10 + a centre that FP64 noise may move
-//      by one cell) is staged into shared memory by ONE TMA 2-D box load.
-//   2. Warps turn it into validity bitmasks with __ballot_sync (one 96-bit row per tile row); from here
-//      on the ring search of GridH.cpp:24-118 is bit arithmetic: a 21-bit window per row, popcounts
-//      for the early-termination rule, find-first-set for the enumeration order.
-//   3. Valid cells are copied to the output tile; masked cells are COMPACTED into a CTA-wide queue
-//      (warp-aggregated shared-memory atomics), so every warp of the search phase is full of real
-//      queries regardless of the mask pattern.
-//   4. One thread per query: termination ring from the bitmasks, candidates in the reference's
-//      enumeration order with their FP64 squared distances (same operation order as GridH.cpp:42-44),
-//      the reference's partial selection sort WITH swaps on a per-thread list in shared memory.
-//      Distances are compared squared; sqrt is monotone, so the order can only differ when two squared
-//      distances are within a few ulps -- those queries (and lists longer than 12) are redone by the
-//      literal per-query path (exact.cuh).  Values of the four picks come from the shared tile.
-//   5. Method epilogue (mean / NN / FP32 IDW weights / FP64 kriging solve), then the whole output
-//      tile is written with coalesced 16-byte stores.
+// FILL = true: full-grid gap fill -- every NaN cell of the grid gets METHOD(query at its own node), valid cells pass
+// through.  This is the structured form of the reference's Grid-B procedure (test_gebco.cpp:150-196: one query per
+// removed cell, built by gridIndexToGeo :72-81, evaluated by GridH::batch*Interpolate, GridH.cpp:160-420) and of
+// BASELINE config 4 (IDW / nearest-neighbour on a 70 % masked grid).  Methods: BILINEAR (four corners, NaN-corner mean:
+// no search), CUBIC (always the ring-search 4-nearest mean here: a masked cell is inside its own 4x4 stencil), KRIGING,
+// NN, IDW, and the opt-in BILINEAR_SEARCH.
+// FILL = false: KRIGING / NN / IDW on an upsampling lattice (test_interpolation.cpp:283-297): every output cell a query.
 //
-// Algorithmic HBM bytes: sizeof(T) read + sizeof(T) written per cell; the kernel is
-// issue-bound (integer/bit work + FP64 distance math), not HBM-bound.
+// Design (one CTA = 256 threads = one 64 x 32 tile of output cells; DESIGN.md section 5.3 has the numbers):
+//   1. The tile's grid cells + a 12-cell halo (88 x 56: search radius 10 + a centre that FP64 noise may move by one
+//      cell) are staged into shared memory by ONE TMA 2-D box load; meanwhile per-axis tables (index-space position,
+//      search centre, squared offsets of the near rings in the reference's operation order) and two small LUTs.
+//   2. Warps turn the block into validity bitmasks with __ballot_sync (one 96-bit row per block row); from here on the
+//      ring search of GridH.cpp:24-118 is bit arithmetic.
+//   3. A warp takes whole tile rows: valid cells go straight to the output, masked cells are COMPACTED into a CTA-wide
+//      queue (popcounts of the warp-uniform row words, one shared atomic per row).
+//   4. Phase A1, one thread per query: the 5 x 5 block around the centre as ONE word whose bit order is the reference's
+//      enumeration order; four popcounts give the pass at which the reference stops, a mask gives its candidates.
+//      Searches that end inside the block with <= 8 candidates take the near path; the others get the general
+//      termination scan (phase A2, rings to radius 10).
+//   5. Records are counting-sorted by (path, candidate count) so that a warp's queries have the same list length.
+//   6. Phase B: warps draw chunks of 32 records from a CTA-wide counter.  Near path: the candidate list lives in
+//      registers (length 4 / 6 / 8 chosen per chunk) and the reference's partial selection sort WITH swaps runs on it
+//      with selects; distances are compared squared and the sorted chain is checked afterwards for a gap that sqrt
+//      rounding could close -- such queries are replayed with the square roots taken first.  General path: list in
+//      shared memory, the selection literally with a sqrt guard per comparison; what it cannot decide goes to the
+//      literal per-query path (exact.cuh).
+//   7. Epilogue on the four picks: mean / first pick / FP32 IDW weights through the SFU reciprocal / kriging (its FP64
+//      solve runs as a phase of its own over the recorded picks).
+//
+// Algorithmic HBM bytes: sizeof(T) read + sizeof(T) written per cell; the kernel is issue-bound (integer /
+// bit work + FP64 distance compares), not HBM-bound.
 #include <cstdlib>
 #include <cstring>
 
