@@ -411,7 +411,11 @@ static cudaError_t launch_tiled(const GridDesc& d, const AxisTables& lat, const 
         bw = (bw + align - 1) / align * align;
     }
     int bh = max_span(lat.h_base, row_begin, row_end, tj, taps, lo, 1);
-    while (static_cast<size_t>(slabs) * bw * bh * es > 96 * 1024 && tj > 8) {   // keep >=2 CTAs/SM of smem
+    // Shared-memory budget per CTA.  Bilinear gains from four CTAs per SM (4 x 56 KB); bicubic re-runs its three-row
+    // horizontal warm-up per row group, so it prefers tall tiles and settles for two or three CTAs (measured:
+    // tools/run_upsample.py, 2x2 / 1x1 / 4x1 / 1x4 on 16384^2).
+    const size_t budget = (METHOD == CUBIC ? 96 : 56) * 1024;
+    while (static_cast<size_t>(slabs) * bw * bh * es > budget && tj > 16) {
         tj /= 2;
         bh = max_span(lat.h_base, row_begin, row_end, tj, taps, lo, 1);
     }
