@@ -151,7 +151,6 @@ struct auvi_grid {
     // lattice host-form staging
     void* d_rows[2] = {nullptr, nullptr};
     size_t d_rows_bytes = 0;
-    // metrics scratch
     std::map<long long, AxisOwned*> axes;             // key: which*2^40 + kind*2^32 + factor
     float last_ms = 0.f;
     int last_tma = 0;
