@@ -674,3 +674,47 @@ def test_tiny_and_ragged_grids_every_path(auvi, shape):
                 if tight: assert bits_equal(got, want), (shape, frac, f, ob.METHOD_NAMES[meth])
                 else: _close(got, want, atol=TIGHT if meth == ob.KRIGING else 1e-3, rtol=0 if meth == ob.KRIGING else 1e-5)
         g.close()
+
+
+@pytest.mark.parametrize("dtype_name", ["f32", "f64"])
+def test_adopted_grid_with_unaligned_pitch_takes_the_plain_load_path(auvi, torch, dtype_name):
+    """An adopted grid whose row pitch is not a multiple of 16 bytes cannot be described by a TMA tensor map: both tiled
+    kernels stage their blocks with plain coalesced loads instead.  Same results as the exact per-query path."""
+    n_lat, n_lon = 333, 1001                                        # 4004 / 8008 bytes per row
+    tdt = torch.float32 if dtype_name == "f32" else torch.float64
+    dt = auvi.F32 if dtype_name == "f32" else auvi.F64
+    jj = torch.arange(n_lat, device="cuda", dtype=torch.float64)[:, None]
+    ii = torch.arange(n_lon, device="cuda", dtype=torch.float64)[None, :]
+    z = (-3000.0 + 700.0 * torch.sin(ii * 0.02) * torch.cos(jj * 0.03) + 0.5 * ii).to(tdt).contiguous()
+    g = auvi.Grid(adopt=dict(ptr=z.data_ptr(), dtype=dt, n_lat=n_lat, n_lon=n_lon, ld=n_lon, row0=0, rows=n_lat, keep=z),
+                  min_lon=10.0, max_lon=12.0, min_lat=50.0, max_lat=51.0)
+    g.mask_hash(0.6, seed=3, count=False)
+    st = torch.cuda.current_stream().cuda_stream
+    a = torch.empty((n_lat, n_lon), dtype=tdt, device="cuda"); b = torch.empty_like(a)
+    sel = torch.empty((n_lat * n_lon, 9), dtype=torch.int32, device="cuda")
+    for meth in (auvi.BILINEAR, auvi.NN, auvi.CUBIC):
+        g.lattice_device(meth, auvi.AXIS_NODES, 1, 1, 1, 0, n_lat, a.data_ptr(), n_lon, None, st)
+        assert not g.uses_tma
+        g.lattice_device(meth, auvi.AXIS_NODES, 1, 1, 1, 0, n_lat, b.data_ptr(), n_lon, sel.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert torch.equal(torch.isnan(a), torch.isnan(b))
+        ok = ~torch.isnan(a)
+        assert torch.equal(a[ok], b[ok]), auvi.METHOD_NAMES[meth]
+    # upsampling lattice, padded output pitch
+    rows, cols = 2 * (n_lat - 1) + 1, 2 * (n_lon - 1) + 1
+    ld = cols + 7
+    u = torch.full((rows, ld), 7.0, dtype=tdt, device="cuda"); v = torch.full_like(u, 7.0)
+    sel2 = torch.empty((rows * cols, 9), dtype=torch.int32, device="cuda")
+    for meth in (auvi.BILINEAR, auvi.CUBIC, auvi.NN):
+        g.lattice_device(meth, auvi.AXIS_EXPANDED, 2, 2, 0, 0, rows, u.data_ptr(), ld, None, st)
+        g.lattice_device(meth, auvi.AXIS_EXPANDED, 2, 2, 0, 0, rows, v.data_ptr(), ld, sel2.data_ptr(), st)
+        torch.cuda.synchronize()
+        same = (u == v) | (torch.isnan(u) & torch.isnan(v))
+        if dtype_name == "f64" or meth == auvi.NN:
+            assert bool(same.all()), auvi.METHOD_NAMES[meth]
+        else:                                                       # FP32 tap weights in the tiled stencils
+            assert torch.equal(torch.isnan(u), torch.isnan(v))
+            ok = ~torch.isnan(u)
+            assert float((u[ok].double() - v[ok].double()).abs().max()) <= 1e-3 + 1e-5 * 4000
+        assert bool((u[:, cols:] == 7.0).all())                     # the padding of the output rows is untouched
+    g.close()
