@@ -679,6 +679,66 @@ int auvi_lattice(auvi_grid* g, int method, int axis_kind, int f_lat, int f_lon, 
     return rc;
 }
 
+// ---- peer memory: gather without a collective -------------------------------------------------------------------
+// One process per GPU.  The consumer exports its result buffer, the producers map it and pass the mapped address as
+// `dev_out` of auvi_lattice_device: the kernel's stores then travel over NVLink themselves.
+
+namespace {
+std::mutex g_peer_mu;
+std::map<void*, void*> g_peer_base;                   // pointer handed out by auvi_peer_open -> base of the IPC mapping
+}
+
+int auvi_peer_export(const void* dev_ptr, unsigned char* handle72) {
+    if (!dev_ptr || !handle72) return fail("null argument");
+    // the IPC handle names the whole allocation: keep the offset of dev_ptr inside it next to the handle
+    typedef CUresult (*range_fn)(CUdeviceptr*, size_t*, CUdeviceptr);
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &sym, cudaEnableDefault, &q) != cudaSuccess || !sym) {
+        cudaGetLastError();
+        return fail("cuMemGetAddressRange is not available");
+    }
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    if (reinterpret_cast<range_fn>(sym)(&base, &size, reinterpret_cast<CUdeviceptr>(dev_ptr)) != CUDA_SUCCESS)
+        return fail("not a device allocation");
+    cudaIpcMemHandle_t h;
+    AUVI_CUDA(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+    static_assert(sizeof h == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle72, &h, 64);
+    const int64_t off = static_cast<int64_t>(reinterpret_cast<CUdeviceptr>(dev_ptr) - base);
+    std::memcpy(handle72 + 64, &off, 8);
+    return 0;
+}
+
+int auvi_peer_open(const unsigned char* handle72, void** out_ptr) {
+    if (!handle72 || !out_ptr) return fail("null argument");
+    cudaIpcMemHandle_t h;
+    int64_t off = 0;
+    std::memcpy(&h, handle72, 64);
+    std::memcpy(&off, handle72 + 64, 8);
+    void* base = nullptr;
+    AUVI_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    *out_ptr = static_cast<char*>(base) + off;
+    std::lock_guard<std::mutex> lk(g_peer_mu);
+    g_peer_base[*out_ptr] = base;
+    return 0;
+}
+
+int auvi_peer_close(void* ptr) {
+    if (!ptr) return 0;
+    void* base = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_peer_mu);
+        auto it = g_peer_base.find(ptr);
+        if (it == g_peer_base.end()) return fail("not a pointer from auvi_peer_open");
+        base = it->second;
+        g_peer_base.erase(it);
+    }
+    AUVI_CUDA(cudaIpcCloseMemHandle(base));
+    return 0;
+}
+
 // ---- metrics ---------------------------------------------------------------------------------------
 
 int auvi_error_metrics_device(const void* dev_truth, const void* dev_est, int dtype, int64_t n,

@@ -52,6 +52,9 @@ SYMBOLS = {
     "auvi_grid_mask_cells": (_i32, [_vp, _vp, _i64, _vp]),
     "auvi_grid_mask_hash": (_i32, [_vp, _dbl, C.c_uint64, C.POINTER(_i64), _vp]),
     "auvi_grid_read": (_i32, [_vp, _i64, _i64, _vp]),
+    "auvi_peer_export": (_i32, [_vp, _vp]),
+    "auvi_peer_open": (_i32, [_vp, C.POINTER(_vp)]),
+    "auvi_peer_close": (_i32, [_vp]),
     "auvi_last_error": (C.c_char_p, []),
     "auvi_last_kernel_ms": (C.c_float, [_vp]),
     "auvi_launch_count": (_i64, []),

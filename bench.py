@@ -454,15 +454,53 @@ def main():
         if rank == 0:
             assert torch.equal(recv[0], sendbuf)
         # The same gather with NO collective call: every rank's upsample kernel stores its tiles straight into rank 0's
-        # buffer over NVLink (peer memory mapped through torch's symmetric memory; the kernel only sees a pointer).
+        # buffer over NVLink (peer memory mapped through the C ABI's CUDA-IPC entries, torch's symmetric memory as the
+        # fallback; the kernel only sees a pointer).
         # Compute and transfer are one kernel: the 16-byte streaming stores of a tile go to the peer while the next
         # tile is computed.
         try:
-            import torch.distributed._symmetric_memory as symm_mem
-            slab = symm_mem.empty((world * g_rows, out_ld), dtype=torch.float32, device=dev)
-            hdl = symm_mem.rendezvous(slab, dist.group.WORLD)
-            root_view = hdl.get_buffer(0, slab.shape, slab.dtype)                  # rank 0's buffer, mapped here
-            dst = root_view.data_ptr() + rank * g_rows * out_ld * 4
+            mapping = "cudaIpc (auvi_peer_export / auvi_peer_open)"
+            opened = None
+            root_view = None
+            # rank 0's buffer mapped into every rank through the C ABI (CUDA IPC), no torch object involved; the two
+            # collectives below are unconditional so that a failure on one rank cannot leave the others waiting
+            import ctypes as C
+            lib = auvi.load()
+            good = 1.0
+            slab = None
+            hbuf = (C.c_ubyte * 72)()
+            if rank == 0:
+                try:
+                    slab = torch.empty((world * g_rows, out_ld), dtype=torch.float32, device=dev)
+                    if lib.auvi_peer_export(slab.data_ptr(), hbuf) != 0:
+                        good = 0.0
+                except Exception:
+                    good = 0.0
+            ht = torch.tensor(list(hbuf), dtype=torch.uint8, device=dev)
+            dist.broadcast(ht, src=0)
+            base_ptr = 0
+            if rank == 0:
+                base_ptr = slab.data_ptr() if slab is not None else 0
+            else:
+                hbuf = (C.c_ubyte * 72)(*ht.cpu().tolist())
+                opened = C.c_void_p()
+                if lib.auvi_peer_open(hbuf, C.byref(opened)) != 0:
+                    good, opened = 0.0, None
+                else:
+                    base_ptr = opened.value
+            flag = torch.tensor([good], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if float(flag.item()) == 0.0:                                              # any rank failed: torch's mapping instead
+                import torch.distributed._symmetric_memory as symm_mem
+                mapping = "torch symmetric memory"
+                if opened is not None:
+                    lib.auvi_peer_close(opened)
+                opened = None
+                slab = symm_mem.empty((world * g_rows, out_ld), dtype=torch.float32, device=dev)
+                hdl = symm_mem.rendezvous(slab, dist.group.WORLD)
+                root_view = hdl.get_buffer(0, slab.shape, slab.dtype)              # rank 0's buffer, mapped here
+                base_ptr = root_view.data_ptr()
+            dst = base_ptr + rank * g_rows * out_ld * 4
 
             def fused():
                 g.lattice_device(auvi.CUBIC, auvi.AXIS_EXPANDED, FACTOR, FACTOR, 0, row_lo, row_lo + g_rows, dst, out_ld, None, stream)
@@ -485,7 +523,9 @@ def main():
             gather["fused_peer_store"] = {
                 "what": "upsample kernel writes its rows into rank 0's buffer over NVLink (no NCCL call, no staging copy)",
                 "ms_compute_plus_transfer": f_ms, "ms_kernel_then_nccl_gather": ms_step * g_rows / my_rows + g_ms,
-                "GBps_into_root": g_bytes / (f_ms * 1e-3) / 1e9, "equals_nccl_gather": bool(ok)}
+                "GBps_into_root": g_bytes / (f_ms * 1e-3) / 1e9, "equals_nccl_gather": bool(ok), "peer_mapping": mapping}
+            if opened is not None:
+                lib.auvi_peer_close(opened)
             del slab, root_view
         except Exception as exc:                                                    # no peer mapping on this box
             gather["fused_peer_store"] = {"unavailable": repr(exc)[:200]}

@@ -158,6 +158,14 @@ int auvi_grid_mask_hash(auvi_grid* g, double fraction, uint64_t seed, int64_t* o
 /* Copy grid rows [row_begin,row_end) back to a dense host array of the grid's dtype. */
 int auvi_grid_read(auvi_grid* g, int64_t row_begin, int64_t row_end, void* host_out);
 
+/* ---- Peer memory (one process per GPU): gather the row shards WITHOUT a collective.  The consumer exports its result
+ *      buffer (any address inside a cudaMalloc allocation), producers map it and pass the mapped address as dev_out of
+ *      auvi_lattice_device: the kernel's 16-byte stores go to the peer over NVLink, compute and transfer are one kernel and no
+ *      staging copy exists (SURVEY.md s8(e) "fusion with the collective").  handle72: 72 bytes to move between processes. */
+int auvi_peer_export(const void* dev_ptr, unsigned char* handle72);
+int auvi_peer_open(const unsigned char* handle72, void** out_ptr);     /* in another process of the same node */
+int auvi_peer_close(void* ptr);                                        /* a pointer returned by auvi_peer_open */
+
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 const char* auvi_last_error(void);          /* thread-local message of the last failure */
 float auvi_last_kernel_ms(const auvi_grid* g); /* device time of the kernels of the last synchronous call */
