@@ -35,8 +35,6 @@ print("torch dense copy device->pinned   %.1f ms" % (ms := t(lambda: h_out.copy_
 part = 8192
 pageable = np.empty((part, cols), dtype=np.float32)
 print("auvi_lattice -> pageable (8192 rows) %.1f ms (%.1f GB/s)" % ((ms := t(lambda: lat(pageable.ctypes.data, 0, part))), part * cols * 4 / ms / 1e6))
-for mb in (64, 1024):
-    os.environ["AUVI_LATTICE_CHUNK_MB"] = str(mb)
 destroy()
 del d, dd
 torch.cuda.empty_cache()
