@@ -69,6 +69,24 @@ def test_argument_validation_messages():
     assert b"null grid handle" in lib.auvi_last_error()
 
 
+def test_peer_and_prep_entries_validate_arguments():
+    lib = auvi.load()
+    buf = (C.c_ubyte * 72)()
+    assert lib.auvi_peer_export(None, buf) != 0 and b"null argument" in lib.auvi_last_error()
+    out = C.c_void_p()
+    assert lib.auvi_peer_open(None, C.byref(out)) != 0 and b"null argument" in lib.auvi_last_error()
+    assert lib.auvi_peer_close(None) == 0
+    h = C.c_void_p()
+    assert lib.auvi_grid_create_raw(None, 3, 1, 1, 1.0, 0.0, auvi.F64, 4, 4, 0.0, 1.0, 0.0, 1.0, 0, C.byref(h)) != 0
+    assert b"null host buffer" in lib.auvi_last_error()
+    assert lib.auvi_grid_create_raw(buf, 9, 1, 1, 1.0, 0.0, auvi.F64, 4, 4, 0.0, 1.0, 0.0, 1.0, 0, C.byref(h)) != 0
+    assert b"raw element type" in lib.auvi_last_error()
+    assert lib.auvi_grid_mask_cells(None, None, 1, None) != 0 and b"null grid handle" in lib.auvi_last_error()
+    if lib.auvi_device_count() == 0:
+        assert lib.auvi_grid_create_csv(b"1,2\n3,4\n", 8, auvi.F64, 0.0, 1.0, 0.0, 1.0, 0, C.byref(h)) != 0
+        assert b"no CUDA device" in lib.auvi_last_error()
+
+
 def test_product_tree_never_touches_the_oracle():
     bad = []
     for base in (PKG, os.path.join(ROOT, "include")):
