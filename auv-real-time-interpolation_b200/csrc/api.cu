@@ -415,12 +415,12 @@ int64_t auvi_launch_count(void) { return g_launches.load(); }
 float auvi_last_kernel_ms(const auvi_grid* g) { return g ? g->last_ms : 0.f; }
 int auvi_uses_tma(const auvi_grid* g) { return g ? g->last_tma : 0; }
 
-int auvi_grid_create(const void* host_rowmajor, int dtype, int64_t n_lat, int64_t n_lon,
-                     double min_lon, double max_lon, double min_lat, double max_lat,
-                     int device, auvi_grid** out) {
+int auvi_grid_create_slab(const void* host_rows, int dtype, int64_t n_lat, int64_t n_lon, int64_t row0, int64_t rows,
+                          double min_lon, double max_lon, double min_lat, double max_lat, int device, auvi_grid** out) {
     if (!out) return fail("null output handle");
     *out = nullptr;
-    if (!host_rowmajor) return fail("null host grid");
+    if (!host_rows) return fail("null host grid");
+    if (row0 < 0 || rows < 1 || row0 + rows > n_lat) return fail("slab rows outside the grid");
     if (auvi_device_count() <= 0) return fail("no CUDA device: libauvi has no CPU fallback");
     auvi_grid* g = new (std::nothrow) auvi_grid;
     if (!g) return fail("out of host memory");
@@ -430,14 +430,23 @@ int auvi_grid_create(const void* host_rowmajor, int dtype, int64_t n_lat, int64_
     // rows padded to a 16-byte pitch so that TMA can address any grid width
     const int64_t ld = (n_lon * es + 15) / 16 * 16 / es;
     cudaError_t e = cudaSetDevice(device);
-    g->owned_bytes = static_cast<size_t>(ld) * n_lat * es;
+    g->owned_bytes = static_cast<size_t>(ld) * rows * es;
     if (e == cudaSuccess) e = cached_malloc(&g->owned, g->owned_bytes, device);
-    if (e == cudaSuccess) e = upload_rows(g->owned, ld * es, host_rowmajor, n_lon * es, n_lat);
+    if (e == cudaSuccess) e = upload_rows(g->owned, ld * es, host_rows, n_lon * es, rows);
     if (e != cudaSuccess) { cudaFree(g->owned); delete g; return fail_cuda("grid upload", e); }
-    g->d.z = g->owned; g->d.ld = ld; g->d.row0 = 0; g->d.rows = g->d.n_lat;
+    g->d.z = g->owned; g->d.ld = ld; g->d.row0 = static_cast<int>(row0); g->d.rows = static_cast<int>(rows);
     if (make_streams(g)) { auvi_grid_destroy(g); return 2; }
     *out = g;
     return 0;
+}
+
+int auvi_grid_create(const void* host_rowmajor, int dtype, int64_t n_lat, int64_t n_lon,
+                     double min_lon, double max_lon, double min_lat, double max_lat,
+                     int device, auvi_grid** out) {
+    if (!out) return fail("null output handle");
+    *out = nullptr;
+    if (!host_rowmajor) return fail("null host grid");
+    return auvi_grid_create_slab(host_rowmajor, dtype, n_lat, n_lon, 0, n_lat, min_lon, max_lon, min_lat, max_lat, device, out);
 }
 
 int auvi_grid_adopt(const void* dev_rows, int dtype, int64_t n_lat, int64_t n_lon, int64_t ld,

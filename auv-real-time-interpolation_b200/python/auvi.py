@@ -31,6 +31,7 @@ AXIS_EXPANDED, AXIS_NODES = 0, 1
 _vp, _i64, _i32, _dbl = C.c_void_p, C.c_int64, C.c_int, C.c_double
 SYMBOLS = {
     "auvi_grid_create": (_i32, [_vp, _i32, _i64, _i64, _dbl, _dbl, _dbl, _dbl, _i32, C.POINTER(_vp)]),
+    "auvi_grid_create_slab": (_i32, [_vp, _i32, _i64, _i64, _i64, _i64, _dbl, _dbl, _dbl, _dbl, _i32, C.POINTER(_vp)]),
     "auvi_grid_adopt": (_i32, [_vp, _i32, _i64, _i64, _i64, _i64, _i64, _dbl, _dbl, _dbl, _dbl, _i32, C.POINTER(_vp)]),
     "auvi_grid_destroy": (_i32, [_vp]),
     "auvi_trim": (_i32, []),

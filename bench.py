@@ -317,23 +317,13 @@ def main():
             # what a caller with host arrays does: upload the slab, run, get every cell back, release
             h = C.c_void_p()
             t0 = time.perf_counter()
-            if world == 1:
-                rc = lib.auvi_grid_create(h_z.data_ptr(), auvi.F32, n_lat_global, n_lon, *bounds, local, C.byref(h))
-                assert rc == 0, lib.auvi_last_error()
-                keep = None
-            else:
-                # a row slab is described by auvi_grid_adopt, which takes device memory: upload it first
-                keep = h_z.to(dev, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-                rc = lib.auvi_grid_adopt(keep.data_ptr(), auvi.F32, n_lat_global, n_lon, n_lon, in_lo, in_hi - in_lo,
-                                         *bounds, local, C.byref(h))
-                assert rc == 0, lib.auvi_last_error()
+            rc = lib.auvi_grid_create_slab(h_z.data_ptr(), auvi.F32, n_lat_global, n_lon, in_lo, in_hi - in_lo, *bounds, local, C.byref(h))
+            assert rc == 0, lib.auvi_last_error()
             t1 = time.perf_counter()
             rc = lib.auvi_lattice(h, auvi.CUBIC, auvi.AXIS_EXPANDED, FACTOR, FACTOR, 0, row_lo, row_lo + e2e_rows, h_out.data_ptr())
             assert rc == 0, lib.auvi_last_error()
             t2 = time.perf_counter()
             lib.auvi_grid_destroy(h)
-            del keep
             t3 = time.perf_counter()
             pieces["upload_ms"] += (t1 - t0) * 1e3; pieces["lattice_ms"] += (t2 - t1) * 1e3; pieces["release_ms"] += (t3 - t2) * 1e3
 
@@ -356,7 +346,7 @@ def main():
         e2e = {"value": e2e_cells / dt / 1e6, "unit": "Mcells/s", "rows_per_rank": e2e_rows, "rows_of_shard": my_rows, "h2d_bytes_per_step": int(h_z.numel() * 4),
                "d2h_bytes_per_step": int(e2e_rows * out_cols * 4), "ms_per_step": dt * 1e3, "steps": e2e_steps,
                "pinned_host": bool(h_out.is_pinned()), "pieces_ms": {k: v / e2e_steps for k, v in pieces.items()},
-               "api": "auvi_grid_create + auvi_lattice(host_out) + auvi_grid_destroy",
+               "api": "auvi_grid_create_slab + auvi_lattice(host_out) + auvi_grid_destroy",
                "cpu_affinity": (f"{numa[0]}-{numa[-1]} ({len(numa)} cores, NVML GPU-local)" if numa else "unbound")}
         # raw pinned device->host copy bandwidth of this box, for context (the e2e step moves 16x more bytes D2H than H2D)
         try:
@@ -375,12 +365,7 @@ def main():
             p_rows = min(e2e_rows, 8192)
             pageable = np.zeros((p_rows, out_cols), dtype=np.float32)             # touched, like a value-initialised vector
             h = C.c_void_p()
-            if world == 1:
-                assert lib.auvi_grid_create(h_z.data_ptr(), auvi.F32, n_lat_global, n_lon, *bounds, local, C.byref(h)) == 0
-                keep = None
-            else:
-                keep = h_z.to(dev)
-                assert lib.auvi_grid_adopt(keep.data_ptr(), auvi.F32, n_lat_global, n_lon, n_lon, in_lo, in_hi - in_lo, *bounds, local, C.byref(h)) == 0
+            assert lib.auvi_grid_create_slab(h_z.data_ptr(), auvi.F32, n_lat_global, n_lon, in_lo, in_hi - in_lo, *bounds, local, C.byref(h)) == 0
             pp = pageable.ctypes.data
             assert lib.auvi_lattice(h, auvi.CUBIC, auvi.AXIS_EXPANDED, FACTOR, FACTOR, 0, row_lo, row_lo + p_rows, pp) == 0
             t0 = time.perf_counter()
@@ -388,7 +373,6 @@ def main():
                 assert lib.auvi_lattice(h, auvi.CUBIC, auvi.AXIS_EXPANDED, FACTOR, FACTOR, 0, row_lo, row_lo + p_rows, pp) == 0
             dtp = (time.perf_counter() - t0) / 2
             lib.auvi_grid_destroy(h)
-            del keep
             e2e["pageable_host"] = {"rows": p_rows, "ms": dtp * 1e3, "GBps_d2h": p_rows * out_cols * 4 / dtp / 1e9,
                                     "Mcells_per_s_this_rank": p_rows * out_cols / dtp / 1e6,
                                     "equals_pinned_result": bool(np.array_equal(pageable[:64], h_out[:64].numpy()))}

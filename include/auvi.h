@@ -43,6 +43,11 @@ int auvi_grid_create(const void* host_rowmajor, int dtype, int64_t n_lat, int64_
                      double min_lon, double max_lon, double min_lat, double max_lat,
                      int device, auvi_grid** out);
 
+/* Upload a row slab of a larger grid: host_rows holds global rows [row0, row0+rows) densely (n_lon elements per row); n_lat
+ * is the GLOBAL row count.  What one rank of a row-sharded job holds: its rows plus the halo. */
+int auvi_grid_create_slab(const void* host_rows, int dtype, int64_t n_lat, int64_t n_lon, int64_t row0, int64_t rows,
+                          double min_lon, double max_lon, double min_lat, double max_lat, int device, auvi_grid** out);
+
 /* Adopt (borrow, never free) a grid -- or a row slab of one -- already resident in device memory.
  * dev_rows holds global rows [row0, row0+rows) with `ld` elements between rows; n_lat is the
  * GLOBAL row count (multi-GPU row sharding: each rank passes its slab + halo). */
