@@ -137,7 +137,9 @@ int auvi_netcdf3_find(const void* file_image, int64_t n_bytes, const char* var_n
 /* Host only: decode a whole variable to doubles (coordinate axes; applies scale_factor / add_offset). */
 int auvi_netcdf3_read_f64(const void* file_image, int64_t n_bytes, const char* var_name, double* out, int64_t n_out);
 /* Host only: out_idx[0..n) = numpy.random.seed(seed); numpy.random.choice(total, n, replace=False)
- * (subset_bathymetry.py:32-39: the legacy MT19937 stream, Fisher-Yates permutation prefix). */
+ * (subset_bathymetry.py:32-39: the legacy MT19937 stream, Fisher-Yates permutation prefix).  Like numpy it permutes all
+ * `total` indices: 8 bytes of host memory per cell, sequential -- meant for GEBCO tiles; at BASELINE config 4's size use
+ * auvi_grid_mask_hash. */
 int auvi_legacy_choice(int64_t total, int64_t n, uint32_t seed, int64_t* out_idx);
 
 /* Upload file-order elements (nc_type 3..6, big- or little-endian) and decode them on the device into a grid of
@@ -149,7 +151,7 @@ int auvi_grid_create_raw(const void* host_raw, int nc_type, int big_endian, int 
 /* A grid from CSV matrix text (one row per latitude, comma separated, "nan" for missing cells: reduced_data.csv of
  * subset_bathymetry.py:78-85, the files readGridCSV parses, test_gebco.cpp:19-40).  The text is uploaded as it is and
  * parsed on the device; every value equals what std::stod returns for the cell.  Rows must have equal field counts.
- * auvi_csv_dims is host only. */
+ * Device scratch while parsing: the text plus 16 bytes per cell.  auvi_csv_dims is host only. */
 int auvi_csv_dims(const char* text, int64_t n_bytes, int64_t* n_rows, int64_t* n_cols);
 int auvi_grid_create_csv(const char* text, int64_t n_bytes, int dtype, double min_lon, double max_lon, double min_lat,
                          double max_lat, int device, auvi_grid** out);
