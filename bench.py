@@ -10,14 +10,18 @@ each rank holds its input row slab + halo; no data-path collective (DESIGN.md "M
 
 One JSON line on rank 0:
   value       output Mcells/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e         same metric through the host-buffer C-ABI call (auvi_grid_create + auvi_lattice):
+  e2e         same metric through the host-buffer C-ABI calls (auvi_grid_create_slab + auvi_lattice + auvi_grid_destroy):
               host->device copy of the grid and device->host copy of every output cell inside the timed region
+              (pinned buffers; `pageable_host` = the same call into ordinary host memory)
+  gather      N > 1 only, outside `value`: NCCL gather of the row shards to rank 0, and the same gather with no
+              collective -- the kernel stores into rank 0's buffer through peer memory (auvi_peer_*)
   roofline    dominant kernel (upsample_tiled_kernel<float,CUBIC>): algorithmic bytes / event time vs
               the measured copy bandwidth in MEASURED_PEAKS.json
   cpu_baseline  the reference's own CPU class (oracle/_ref, GridH::batchCubicInterpolate) on a bounded
               row block of the same lattice, all host threads
-  extra       the other methods / BASELINE configs (bilinear upsample, gap-fill methods on a 70 % masked
-              grid, Mariana 50 % through the Point-list API with RMSE) -- informational
+  extra       the other methods / BASELINE configs (bilinear and latitude-only upsample, every gap-fill method on a
+              70 % masked grid incl. the stated 65536^2 one -- row-sharded over the ranks when N > 1 --, Mariana 50 %
+              through the Point-list API with RMSE, Grid A points and 2x lattice) -- informational
 `--impl reference` times only the reference CPU implementation on the same config and metric.
 """
 import argparse
