@@ -24,9 +24,8 @@
 #include <string>
 #include <vector>
 
-#include <omp.h>
-
 #include "../../include/auvi.h"
+#include "hostpool.h"
 #include "launch.h"
 
 using namespace auvi;
@@ -72,6 +71,7 @@ struct AxisOwned {
 struct DevBlock { void* p; size_t bytes; int device; };
 std::mutex g_cache_mu;
 std::vector<DevBlock> g_cache;
+std::map<void*, size_t> g_block_bytes;          // every live block handed out by cached_malloc -> the size it was ALLOCATED with
 size_t g_cache_held = 0;
 constexpr size_t kCacheBytes = 6ull << 30;
 constexpr size_t kCacheMinBlock = 4ull << 10;
@@ -86,6 +86,7 @@ cudaError_t cached_malloc(void** out, size_t bytes, int device) {
         if (best != g_cache.size()) {
             *out = g_cache[best].p;
             g_cache_held -= g_cache[best].bytes;
+            g_block_bytes[*out] = g_cache[best].bytes;              // a reused block keeps its real size
             g_cache.erase(g_cache.begin() + best);
             return cudaSuccess;
         }
@@ -98,14 +99,22 @@ cudaError_t cached_malloc(void** out, size_t bytes, int device) {
         g_cache.clear(); g_cache_held = 0;
         e = cudaMalloc(out, bytes);
     }
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        g_block_bytes[*out] = bytes;
+    }
     return e;
 }
 
-// `bytes` must be the size the block was allocated with (callers keep it); it may exceed the size asked for.
-void cached_free(void* p, size_t bytes, int device) {
+// The block goes back to the cache under the size it was allocated with (a reused block may be up to 25 % larger than
+// what its last user asked for), so the 6 GiB cap counts real memory.  `asked` is only a fallback for foreign pointers.
+void cached_free(void* p, size_t asked, int device) {
     if (!p) return;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    size_t bytes = asked;
+    auto it = g_block_bytes.find(p);
+    if (it != g_block_bytes.end()) { bytes = it->second; g_block_bytes.erase(it); }
     if (bytes >= kCacheMinBlock && bytes <= kCacheBytes) {
-        std::lock_guard<std::mutex> lk(g_cache_mu);
         while (!g_cache.empty() && g_cache_held + bytes > kCacheBytes) {   // evict oldest
             cudaFree(g_cache.front().p);
             g_cache_held -= g_cache.front().bytes;
@@ -115,6 +124,13 @@ void cached_free(void* p, size_t bytes, int device) {
         g_cache_held += bytes;
         return;
     }
+    cudaFree(p);
+}
+
+// A block that must not be reused (an error left work in flight on it): plain cudaFree, bookkeeping dropped.
+void uncached_free(void* p) {
+    if (!p) return;
+    { std::lock_guard<std::mutex> lk(g_cache_mu); g_block_bytes.erase(p); }
     cudaFree(p);
 }
 
@@ -254,7 +270,7 @@ struct MetricsScratch {
         if (e == cudaSuccess) e = cudaMemcpyAsync(h, result5, sizeof h, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e == cudaSuccess) { cached_free(scratch, bytes, device); return 0; }
-        cudaFree(scratch);
+        uncached_free(scratch);
         return fail_cuda("metrics", e);
     }
 };
@@ -348,8 +364,7 @@ cudaError_t upload_rows(void* dev, size_t dev_pitch, const void* host, size_t ro
     cudaEvent_t ev[2] = {nullptr, nullptr};
     cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
-    const int hw = omp_get_max_threads();
-    const int nt = hw < 16 ? (hw < 1 ? 1 : hw) : 16;
+    HostPool& pool = HostPool::get();
     int64_t c = 0;
     for (int64_t r = 0; r < n_rows && e == cudaSuccess; r += stage_rows, ++c) {
         const int b = static_cast<int>(c & 1);
@@ -357,12 +372,10 @@ cudaError_t upload_rows(void* dev, size_t dev_pitch, const void* host, size_t ro
         if (c >= 2) e = cudaEventSynchronize(ev[b]);
         if (e != cudaSuccess) break;
         const char* src = static_cast<const char*>(host) + static_cast<size_t>(r) * row_bytes;
-        const int64_t bytes = cnt * static_cast<int64_t>(row_bytes), piece = (bytes / nt + 4095) & ~4095ll;
-#pragma omp parallel for schedule(static) num_threads(nt)
-        for (int t = 0; t < nt; ++t) {
-            const int64_t at = t * piece, len = at + piece <= bytes ? piece : bytes - at;
-            if (len > 0) std::memcpy(ring[b] + at, src + at, static_cast<size_t>(len));
-        }
+        char* const dst = ring[b];
+        pool.for_range(cnt * static_cast<int64_t>(row_bytes), pool.size(), 4096, [&](int64_t lo, int64_t hi) {
+            std::memcpy(dst + lo, src + lo, static_cast<size_t>(hi - lo));
+        });
         e = cudaMemcpy2DAsync(static_cast<char*>(dev) + static_cast<size_t>(r) * dev_pitch, dev_pitch, ring[b], row_bytes, row_bytes,
                               static_cast<size_t>(cnt), cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaEventRecord(ev[b], st);
@@ -377,8 +390,8 @@ cudaError_t upload_rows(void* dev, size_t dev_pitch, const void* host, size_t ro
 // Host threads for packing / unpacking point records (memory-bound loops): a few are enough to reach the copy rate.
 int pack_threads(int64_t cnt) {
     if (cnt < 32768) return 1;
-    const int hw = omp_get_max_threads();
-    return hw < 8 ? (hw < 1 ? 1 : hw) : 8;
+    const int hw = HostPool::get().size();
+    return hw < 8 ? hw : 8;
 }
 
 }  // namespace
@@ -433,7 +446,7 @@ int auvi_grid_create_slab(const void* host_rows, int dtype, int64_t n_lat, int64
     g->owned_bytes = static_cast<size_t>(ld) * rows * es;
     if (e == cudaSuccess) e = cached_malloc(&g->owned, g->owned_bytes, device);
     if (e == cudaSuccess) e = upload_rows(g->owned, ld * es, host_rows, n_lon * es, rows);
-    if (e != cudaSuccess) { cudaFree(g->owned); delete g; return fail_cuda("grid upload", e); }
+    if (e != cudaSuccess) { uncached_free(g->owned); delete g; return fail_cuda("grid upload", e); }
     g->d.z = g->owned; g->d.ld = ld; g->d.row0 = static_cast<int>(row0); g->d.rows = static_cast<int>(rows);
     if (make_streams(g)) { auvi_grid_destroy(g); return 2; }
     *out = g;
@@ -512,8 +525,17 @@ int auvi_interp_points_device(auvi_grid* g, int method, const void* dev_pts, int
     return 0;
 }
 
-int auvi_interp_points(auvi_grid* g, int method, const void* host_pts, int64_t n,
-                       int64_t stride_bytes, void* host_out, int64_t out_stride_bytes) {
+// On an error exit copies and kernels of earlier chunks may still be in flight on the staging buffers the next call
+// reuses: wait for both streams before handing the error back.
+static void quiesce(auvi_grid* g) {
+    const std::string keep = t_error;
+    for (int k = 0; k < 2; ++k) if (g && g->st[k]) cudaStreamSynchronize(g->st[k]);
+    cudaGetLastError();
+    t_error = keep;
+}
+
+static int interp_points_host(auvi_grid* g, int method, const void* host_pts, int64_t n,
+                              int64_t stride_bytes, void* host_out, int64_t out_stride_bytes) {
     if (check_common(g, method)) return 1;
     if (n < 0) return fail("negative point count");
     if (n == 0) return 0;                                        // GridD.cu:96-98: nothing to do
@@ -537,9 +559,9 @@ int auvi_interp_points(auvi_grid* g, int method, const void* host_pts, int64_t n
         AUVI_CUDA(cudaEventSynchronize(g->ev_done[b]));
         const double* r = g->h_out[b];
         double* const d0 = dst + lo * od;
-        const int nt = pack_threads(cnt);
-#pragma omp parallel for schedule(static) num_threads(nt) if (nt > 1)
-        for (int64_t k = 0; k < cnt; ++k) d0[k * od] = r[k];
+        HostPool::get().for_range(cnt, pack_threads(cnt), 1024, [&](int64_t k0, int64_t k1) {
+            for (int64_t k = k0; k < k1; ++k) d0[k * od] = r[k];
+        });
         float ms = 0.f;
         AUVI_CUDA(cudaEventElapsedTime(&ms, g->ev_k0[b], g->ev_k1[b]));
         ms_total += ms;
@@ -551,9 +573,9 @@ int auvi_interp_points(auvi_grid* g, int method, const void* host_pts, int64_t n
         if (c >= 2 && drain(c - 2)) return 2;                     // buffer b is free again after this
         double* pin = g->h_in[b];
         const double* s = src + lo * sd;
-        const int nt = pack_threads(cnt);
-#pragma omp parallel for schedule(static) num_threads(nt) if (nt > 1)
-        for (int64_t k = 0; k < cnt; ++k) { pin[2 * k] = s[k * sd]; pin[2 * k + 1] = s[k * sd + 1]; }
+        HostPool::get().for_range(cnt, pack_threads(cnt), 1024, [&](int64_t k0, int64_t k1) {
+            for (int64_t k = k0; k < k1; ++k) { pin[2 * k] = s[k * sd]; pin[2 * k + 1] = s[k * sd + 1]; }
+        });
         cudaStream_t st = g->st[b];
         AUVI_CUDA(cudaMemcpyAsync(g->d_in[b], pin, sizeof(double) * 2 * cnt, cudaMemcpyHostToDevice, st));
         AUVI_CUDA(cudaEventRecord(g->ev_k0[b], st));
@@ -568,6 +590,13 @@ int auvi_interp_points(auvi_grid* g, int method, const void* host_pts, int64_t n
         if (drain(c)) return 2;
     g->last_ms = ms_total;
     return 0;
+}
+
+int auvi_interp_points(auvi_grid* g, int method, const void* host_pts, int64_t n,
+                       int64_t stride_bytes, void* host_out, int64_t out_stride_bytes) {
+    const int rc = interp_points_host(g, method, host_pts, n, stride_bytes, host_out, out_stride_bytes);
+    if (rc) quiesce(g);
+    return rc;
 }
 
 // ---- lattice ---------------------------------------------------------------------------------------
@@ -653,14 +682,11 @@ int auvi_lattice(auvi_grid* g, int method, int axis_kind, int f_lat, int f_lon, 
         if (pageable) {
             char* const dst = static_cast<char*>(host_out) + (lo_of[b] - row_begin) * row_bytes;
             const int64_t bytes = (hi_of[b] - lo_of[b]) * row_bytes;
-            const int hw = omp_get_max_threads();
-            const int nt = bytes < (1 << 20) ? 1 : (hw < 16 ? (hw < 1 ? 1 : hw) : 16);   // a plain copy: bandwidth-bound, more threads help
-            const int64_t piece = (bytes / nt + 4095) & ~4095ll;
-#pragma omp parallel for schedule(static) num_threads(nt) if (nt > 1)
-            for (int t = 0; t < nt; ++t) {
-                const int64_t at = t * piece, len = at + piece <= bytes ? piece : bytes - at;
-                if (len > 0) std::memcpy(dst + at, bounce[b] + at, static_cast<size_t>(len));
-            }
+            HostPool& pool = HostPool::get();                          // a plain copy: bandwidth-bound, more threads help
+            const char* const from = bounce[b];
+            pool.for_range(bytes, bytes < (1 << 20) ? 1 : pool.size(), 4096, [&](int64_t lo, int64_t hi) {
+                std::memcpy(dst + lo, from + lo, static_cast<size_t>(hi - lo));
+            });
         }
         float ms = 0.f;
         AUVI_CUDA(cudaEventElapsedTime(&ms, g->ev_k0[b], g->ev_k1[b]));
@@ -683,6 +709,7 @@ int auvi_lattice(auvi_grid* g, int method, int axis_kind, int f_lat, int f_lon, 
         if (e != cudaSuccess) { rc = fail_cuda("lattice copy", e); break; }
     }
     for (int64_t k = (c >= 2 ? c - 2 : 0); k < c && !rc; ++k) rc = drain(static_cast<int>(k & 1));
+    if (rc) quiesce(g);
     if (pageable) { cudaDeviceSynchronize(); release_bounce(bounce, need); }
     g->last_ms = ms_total;
     return rc;
@@ -826,7 +853,7 @@ int auvi_grid_create_raw(const void* host_raw, int nc_type, int big_endian, int 
                                                 g->owned, ld, dtype, nullptr);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (d_raw) cached_free(d_raw, raw_bytes, device);
-    if (e != cudaSuccess) { cudaFree(g->owned); delete g; return fail_cuda("raw grid upload", e); }
+    if (e != cudaSuccess) { uncached_free(g->owned); delete g; return fail_cuda("raw grid upload", e); }
     g_launches.fetch_add(1);
     g->d.z = g->owned; g->d.ld = ld; g->d.row0 = 0; g->d.rows = g->d.n_lat;
     if (make_streams(g)) { auvi_grid_destroy(g); return 2; }
@@ -930,7 +957,7 @@ int auvi_grid_create_csv(const char* text, int64_t n_bytes, int dtype, double mi
     }
     e = cudaDeviceSynchronize();
     release(false);
-    if (e != cudaSuccess) { cudaFree(g->owned); delete g; return fail_cuda("CSV parse", e); }
+    if (e != cudaSuccess) { uncached_free(g->owned); delete g; return fail_cuda("CSV parse", e); }
     g->d.z = g->owned; g->d.ld = ld; g->d.row0 = 0; g->d.rows = g->d.n_lat;
     if (make_streams(g)) { auvi_grid_destroy(g); return 2; }
     *out = g;

@@ -326,17 +326,27 @@ __device__ __forceinline__ void nearest_first(Picked& p) {          // found < 4
     }
 }
 
+__device__ __forceinline__ float rcp_sfu(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
 // IDW power 2 over min(found,4) picks.  Weights in FP32 through the SFU reciprocal (north_star:
 // "FP32 FMA/SFU distance-weight math"); the SELECTION above stays FP64-exact.  d == 0 -> that value.
-__device__ __forceinline__ double idw_from_picked(const Picked& p) {
+// The weight of a pick is rcp(float(d^2)) with d^2 the squared index-space distance formed exactly as the search
+// forms it before its sqrt (GridH.cpp:42-44) -- the same expression, on the same bits, as the tiled kernel
+// (fill.cu finish_four), so the point-list and the lattice entry points return identical IDW values.
+__device__ __forceinline__ double idw_from_picked(const Picked& p, double x, double y) {
     int m = p.found < 4 ? p.found : 4;
     float num = 0.f, den = 0.f;
     // centre the values so the FP32 weighted mean keeps ~1e-7 relative accuracy on 10 km depths
     const double ref = p.v[0];
     for (int k = 0; k < m; ++k) {
         if (p.d[k] == 0.0) return p.v[k];
-        float d = static_cast<float>(p.d[k]);
-        float w = __frcp_rn(d * d);
+        const double ddi = dsub(dadd(static_cast<double>(p.i[k]), 0.5), x);
+        const double ddj = dsub(dadd(static_cast<double>(p.j[k]), 0.5), y);
+        const float w = rcp_sfu(static_cast<float>(dadd(dmul(ddi, ddi), dmul(ddj, ddj))));
         num = fmaf(w, static_cast<float>(p.v[k] - ref), num);
         den += w;
     }
@@ -374,7 +384,7 @@ __device__ double interp_exact(const GridView<T>& g, int method, double lon, dou
         if (p.found < 4) nearest_first(p);
         out = p.found > 0 ? p.v[0] : qnan();
     } else {
-        out = p.found > 0 ? idw_from_picked(p) : qnan();
+        out = p.found > 0 ? idw_from_picked(p, x, y) : qnan();
     }
     if (sel) *sel = p;
     return out;

@@ -131,12 +131,6 @@ __device__ __forceinline__ double sq_offset(double cf, int d, double q) {
     return dmul(t, t);
 }
 
-__device__ __forceinline__ float rcp_sfu(float v) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
-
 // ---- helper: selection in registers ------------------------------------------------------------------------------
 // The reference's partial selection sort with swaps (GridH.cpp:123-140) on a list of N (distance, cell) pairs held
 // in registers: pass m finds the FIRST strict minimum of entries m..N-1 and swaps it with entry m.  Cells are
@@ -281,7 +275,10 @@ __device__ __forceinline__ bool near_query(FillSmem<T>& s, const FillParams<T>& 
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         v[e] = centre[s.cell_tile[c[e]]];
-        d2[e] = REPLAY ? dmul(d[e], d[e]) : d[e];
+        if (REPLAY) {                                               // the squared distance as first formed, not sqrt(.)^2
+            const uint32_t off = s.cell_off[c[e]];
+            d2[e] = dadd(*reinterpret_cast<const double*>(sqx + (off & 0xffffu)), *reinterpret_cast<const double*>(sqy + (off >> 16)));
+        } else d2[e] = d[e];
     }
     __stcs(out_tile + lj * p.out_ld + li, finish_four<T, METHOD>(p, v, d2, pi, pj, I0 + li, J0 + lj));
     return true;

@@ -51,6 +51,7 @@ struct Attr { std::string name; int type; int64_t nelems; int64_t at; };
 bool read_attrs(Reader& r, std::vector<Attr>* out) {
     const uint32_t tag = r.u32(), cnt = r.u32();
     if (!r.ok || (tag != 0 && tag != 0x0C) || (tag == 0 && cnt != 0)) return false;
+    if (static_cast<int64_t>(cnt) * 12 > r.n - r.at) return false;   // an attribute takes at least 12 header bytes
     for (uint32_t k = 0; k < cnt; ++k) {
         Attr a;
         a.name = r.name();
@@ -58,7 +59,7 @@ bool read_attrs(Reader& r, std::vector<Attr>* out) {
         a.nelems = r.u32();
         a.at = r.at;
         const int ts = type_size(a.type);
-        if (!r.ok || ts == 0) return false;
+        if (!r.ok || ts == 0 || a.nelems * ts > r.n - r.at) return false;
         r.skip(a.nelems * ts);
         if (!r.ok) return false;
         if (out) out->push_back(a);
@@ -130,14 +131,18 @@ int auvi_netcdf3_find(const void* file_image, int64_t n_bytes, const char* var_n
     {
         const uint32_t tag = r.u32(), cnt = r.u32();
         if (!r.ok || (tag != 0 && tag != 0x0A)) return auvi::set_error("corrupt NetCDF header (dimension list)");
-        for (uint32_t k = 0; k < cnt; ++k) { r.name(); dim_len.push_back(r.u32()); }
+        // counts come from the (untrusted) file: a dimension entry takes at least 8 header bytes
+        if (static_cast<int64_t>(cnt) * 8 > r.n - r.at) return auvi::set_error("corrupt NetCDF header (dimension count)");
+        for (uint32_t k = 0; k < cnt && r.ok; ++k) { r.name(); dim_len.push_back(r.u32()); }
     }
     if (!r.ok || !read_attrs(r, nullptr)) return auvi::set_error("corrupt NetCDF header (global attributes)");
     const uint32_t tag = r.u32(), n_vars = r.u32();
     if (!r.ok || (tag != 0 && tag != 0x0B)) return auvi::set_error("corrupt NetCDF header (variable list)");
+    if (static_cast<int64_t>(n_vars) * 24 > r.n - r.at) return auvi::set_error("corrupt NetCDF header (variable count)");
     for (uint32_t v = 0; v < n_vars; ++v) {
         const std::string name = r.name();
         const uint32_t ndims = r.u32();
+        if (!r.ok || static_cast<int64_t>(ndims) * 4 > r.n - r.at) return auvi::set_error("corrupt NetCDF header (variable entry)");
         std::vector<uint32_t> ids;
         for (uint32_t k = 0; k < ndims; ++k) ids.push_back(r.u32());
         std::vector<Attr> attrs;
@@ -156,6 +161,7 @@ int auvi_netcdf3_find(const void* file_image, int64_t n_bytes, const char* var_n
             if (ids[k] >= dim_len.size()) return auvi::set_error("corrupt NetCDF header (dimension id)");
             if (dim_len[ids[k]] == 0) return auvi::set_error("record (unlimited-dimension) variables are not supported");
             out->shape[k] = dim_len[ids[k]];
+            if (out->shape[k] > (int64_t(1) << 40) / out->n_elems) return auvi::set_error("variable too large");   // no int64 overflow
             out->n_elems *= out->shape[k];
         }
         out->data_offset = begin;
@@ -166,7 +172,7 @@ int auvi_netcdf3_find(const void* file_image, int64_t n_bytes, const char* var_n
             if (a.name == "add_offset") out->add_offset = decode_be(r.p + a.at, a.type);
             if (a.name == "_FillValue") { out->has_fill = 1; out->fill_value = decode_be(r.p + a.at, a.type); }
         }
-        if (out->elem_bytes == 0 || begin < 0 || begin + out->n_elems * out->elem_bytes > n_bytes)
+        if (out->elem_bytes == 0 || begin < 0 || begin > n_bytes || out->n_elems > (n_bytes - begin) / out->elem_bytes)
             return auvi::set_error("variable data lies outside the file image");
         return 0;
     }

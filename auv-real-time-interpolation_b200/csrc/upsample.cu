@@ -61,6 +61,7 @@ struct TileParams {
                                    // (incl. its own stencil halo), when one box would exceed the 256-element TMA limit
     int use_tma;
     int vec_ok;                    // out and out_ld are 16-byte aligned: vector stores allowed
+    int rows_lo, rows_hi;          // global rows [lo,hi) resident in g.z (a row slab of a sharded grid)
 };
 
 __device__ __forceinline__ void cr_weights(float t, float& w0, float& w1, float& w2, float& w3) {
@@ -145,6 +146,9 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
             for (int k = tid; k < box_elems; k += kTileThreads) {  // coalesced, clamp-to-edge
                 int lr = k / bw, lc = k - lr * bw;
                 int gr = clampi(r0 + lr, 0, p.g.n_lat - 1), gc = clampi(c0 + lc, 0, p.g.n_lon - 1);
+                // bh is the worst-case span over all tiles: a box may reach past the rows this tile uses -- and past
+                // the resident slab.  Such rows are never read by the stencil; stay inside the allocation.
+                gr = clampi(gr, p.rows_lo, p.rows_hi - 1);
                 tile[sl * box_stride + k] = __ldg(p.g.z + static_cast<int64_t>(gr - p.g.row0) * p.g.ld + gc);
             }
         }
@@ -436,6 +440,7 @@ static cudaError_t launch_tiled(const GridDesc& d, const AxisTables& lat, const 
     p.tj = tj; p.bw = bw; p.bh = bh; p.slabs = slabs;
     p.box_stride = static_cast<int>((static_cast<size_t>(bw) * bh * es + 127) / 128 * 128 / es);
     p.vec_ok = (reinterpret_cast<uintptr_t>(out) % 16 == 0 && (out_ld * es) % 16 == 0) ? 1 : 0;
+    p.rows_lo = d.row0; p.rows_hi = d.row0 + d.rows;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
     // The tensor map covers the resident slab; box rows outside it are zero-filled.  The slab check

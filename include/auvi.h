@@ -125,7 +125,8 @@ typedef struct auvi_nc_var {
     int32_t nc_type;       /* 1 byte, 2 char, 3 short, 4 int, 5 float, 6 double */
     int32_t elem_bytes;
     int32_t ndims;
-    int32_t has_fill;
+    int32_t has_fill;      /* _FillValue attribute present (reported only: the decoders do not map it to NaN --
+                            * GEBCO tiles carry no missing cells; mask with auvi_grid_mask_cells / _hash) */
     int64_t shape[4];
     int64_t n_elems;
     int64_t data_offset;   /* bytes from the start of the file image; elements are big-endian, row-major */

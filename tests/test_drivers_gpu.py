@@ -34,10 +34,11 @@ def _write_matrix_csv(fn, z):
             f.write(",".join("nan" if np.isnan(v) else repr(float(v)) for v in row) + "\n")
 
 
-def test_test_gebco_runs_unchanged(tmp_path):
+@pytest.mark.parametrize("tile,frac", [("mid_atlantic", 0.10), ("mariana", 0.50)])   # the second is BASELINE configs[1] verbatim
+def test_test_gebco_runs_unchanged(tmp_path, tile, frac):
     from oracle import binding as ob
     exe = _need("test_gebco")
-    case = ob.masked_case("mid_atlantic", 0.10)
+    case = ob.masked_case(tile, frac)
     data = tmp_path / "C:" / "College" / "EdgeComputing" / "code" / "test_data"
     res = tmp_path / "C:" / "College" / "EdgeComputing" / "results"
     data.mkdir(parents=True)

@@ -264,13 +264,16 @@ def test_gap_fill_nodes_matches_oracle(auvi, torch, name, frac):
     g.close()
 
 
-def test_row_slabs_equal_whole_grid(auvi, torch):
-    """Two row slabs with halos (what two ranks hold) reproduce the single-GPU result bit for bit."""
+@pytest.mark.parametrize("ld", [260, 261])
+def test_row_slabs_equal_whole_grid(auvi, torch, ld):
+    """Two row slabs with halos (what two ranks hold) reproduce the single-GPU result bit for bit.  ld = 261 gives the
+    slabs a row pitch TMA cannot address: the plain-load staging path, whose boxes must stay inside the slab."""
     z = ob.synth_grid(301, 260).astype(np.float32)
     z.ravel()[np.random.RandomState(8).choice(z.size, 3000, replace=False)] = np.nan
     bounds = (0.0, 2.0, 40.0, 43.0)
     whole = auvi.Grid(z, *bounds)
-    dz = torch.from_numpy(z).cuda()
+    dz = torch.full((301, ld), float("nan"), dtype=torch.float32, device="cuda")
+    dz[:, :260] = torch.from_numpy(z).cuda()
     halo = 12
     for meth, kind, f, fill in ((auvi.CUBIC, auvi.AXIS_EXPANDED, 4, 0), (auvi.BILINEAR, auvi.AXIS_EXPANDED, 4, 0),
                                 (auvi.IDW, auvi.AXIS_NODES, 1, 1), (auvi.KRIGING, auvi.AXIS_NODES, 1, 1)):
@@ -282,16 +285,17 @@ def test_row_slabs_equal_whole_grid(auvi, torch):
             in_lo = max(0, lo // f - halo)
             in_hi = min(301, (hi - 1) // f + 1 + halo + 1)
             slab = dz[in_lo:in_hi]
-            g = auvi.Grid(adopt=dict(ptr=slab.data_ptr(), dtype=auvi.F32, n_lat=301, n_lon=260, ld=260, row0=in_lo,
+            g = auvi.Grid(adopt=dict(ptr=slab.data_ptr(), dtype=auvi.F32, n_lat=301, n_lon=260, ld=ld, row0=in_lo,
                                      rows=in_hi - in_lo, keep=slab), min_lon=bounds[0], max_lon=bounds[1],
                           min_lat=bounds[2], max_lat=bounds[3])
             parts.append(g.lattice(meth, kind, f, f, fill=fill, row_begin=lo, row_end=hi))
+            assert bool(g.uses_tma) == (ld % 4 == 0)
             g.close()
         got = np.concatenate(parts, axis=0)
         assert bits_equal(got.astype(np.float64), ref.astype(np.float64)), auvi.METHOD_NAMES[meth]
     # a slab without enough halo is refused, not silently wrong
     slab = dz[100:200]
-    g = auvi.Grid(adopt=dict(ptr=slab.data_ptr(), dtype=auvi.F32, n_lat=301, n_lon=260, ld=260, row0=100, rows=100,
+    g = auvi.Grid(adopt=dict(ptr=slab.data_ptr(), dtype=auvi.F32, n_lat=301, n_lon=260, ld=ld, row0=100, rows=100,
                              keep=slab), min_lon=bounds[0], max_lon=bounds[1], min_lat=bounds[2], max_lat=bounds[3])
     with pytest.raises(auvi.AuviError, match="halo"):
         g.lattice(auvi.IDW, auvi.AXIS_NODES, 1, 1, fill=1, row_begin=100, row_end=200)

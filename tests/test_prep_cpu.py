@@ -103,3 +103,29 @@ def test_csv_dims_host_only():
     assert dims(b"1,nan\n2,3\n\n\n") == (0, 2, 2)               # trailing blank lines are not rows
     rc, _, _ = dims(b"\n\n")
     assert rc != 0 and b"Grid data is empty" in lib.auvi_last_error()
+
+
+def test_netcdf3_header_counts_are_bounded(tmp_path):
+    """The header's counts come from an untrusted file: truncated images and crafted counts (2^32 - 1 dimensions,
+    variables or attribute elements; a shape whose product overflows int64) fail cleanly instead of looping or allocating."""
+    import struct
+    elev = np.arange(6, dtype="i2").reshape(2, 3)
+    path = str(tmp_path / "t.nc")
+    _write_nc(path, 1, elev, np.array([0.0, 1.0]), np.array([0.0, 1.0, 2.0]))
+    img = open(path, "rb").read()
+    v = auvi.netcdf3_find(img, "elevation")
+    assert v.n_elems == 6
+    for cut in range(8, v.data_offset + 12, 7):                          # every truncation inside the header or the data
+        with pytest.raises(auvi.AuviError):
+            auvi.netcdf3_find(img[:cut], "elevation")
+    huge = struct.pack(">I", 0xFFFFFFFF)
+    bad_dims = img[:12] + huge + img[16:]                           # dimension count
+    with pytest.raises(auvi.AuviError, match="corrupt NetCDF header"):
+        auvi.netcdf3_find(bad_dims, "elevation")
+    # both dimension lengths 2^31: the element count must not wrap into something that passes the size check
+    at = img.index(b"lat\x00") + 4
+    big = img[:at] + struct.pack(">I", 0x80000000) + img[at + 4:]
+    at = big.index(b"lon\x00") + 4
+    big = big[:at] + struct.pack(">I", 0x80000000) + big[at + 4:]
+    with pytest.raises(auvi.AuviError):
+        auvi.netcdf3_find(big, "elevation")
