@@ -364,7 +364,7 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-bool make_grid_tensor_map(const GridDesc& d, int box_w, int box_h, CUtensorMap* out) {
+bool make_grid_tensor_map(const GridDesc& d, int box_w, int box_h, CUtensorMap* out, bool nan_fill) {
     const size_t es = d.dtype == DT_F64 ? 8 : 4;
     static const bool disabled = getenv("AUVI_NO_TMA") != nullptr;       // debugging / A-B measurements only
     if (disabled) return false;
@@ -380,7 +380,7 @@ bool make_grid_tensor_map(const GridDesc& d, int box_w, int box_h, CUtensorMap* 
     CUresult r = fn(out, d.dtype == DT_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                     const_cast<void*>(d.z), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    nan_fill ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
