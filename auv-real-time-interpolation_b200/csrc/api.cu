@@ -315,33 +315,41 @@ int ensure_point_staging(auvi_grid* g) {
     return 0;
 }
 
-// Pinned bounce ring of the lattice host form (pageable destinations), one per process, grown on demand.
+// Pinned bounce rings of the lattice host form (pageable destinations) and of the pageable grid upload: a process-wide
+// pool, so that neither a caller that makes one call after another nor several host threads driving several devices
+// (multi.cu) pin and unpin 128 MiB per call.  auvi_trim() releases the idle ones.
+struct BounceRing { char* buf[2]; size_t bytes; };
 std::mutex g_bounce_mu;
-char* g_bounce[2] = {nullptr, nullptr};
-size_t g_bounce_bytes = 0;
-bool g_bounce_busy = false;
+std::vector<BounceRing> g_bounce_free;
 
-int acquire_bounce(size_t need, char* (&out)[2]) {
-    std::lock_guard<std::mutex> lk(g_bounce_mu);
-    if (g_bounce_busy) {                                           // another thread is in a lattice call: private ring
-        for (int k = 0; k < 2; ++k) AUVI_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&out[k]), need, cudaHostAllocDefault));
-        return 0;
+int acquire_bounce(size_t& need, char* (&out)[2]) {   // `need` comes back as the ring's real stage size
+    {
+        std::lock_guard<std::mutex> lk(g_bounce_mu);
+        for (size_t k = 0; k < g_bounce_free.size(); ++k)
+            if (g_bounce_free[k].bytes >= need) {
+                out[0] = g_bounce_free[k].buf[0]; out[1] = g_bounce_free[k].buf[1];
+                need = g_bounce_free[k].bytes;
+                g_bounce_free.erase(g_bounce_free.begin() + k);
+                return 0;
+            }
+        if (!g_bounce_free.empty()) {                              // too small: replace it rather than keep both
+            cudaFreeHost(g_bounce_free.back().buf[0]); cudaFreeHost(g_bounce_free.back().buf[1]);
+            g_bounce_free.pop_back();
+        }
     }
-    if (need > g_bounce_bytes) {
-        for (int k = 0; k < 2; ++k) { if (g_bounce[k]) cudaFreeHost(g_bounce[k]); g_bounce[k] = nullptr; }
-        g_bounce_bytes = 0;
-        for (int k = 0; k < 2; ++k) AUVI_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_bounce[k]), need, cudaHostAllocDefault));
-        g_bounce_bytes = need;
+    out[0] = out[1] = nullptr;
+    for (int k = 0; k < 2; ++k) {
+        const cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&out[k]), need, cudaHostAllocPortable);
+        if (e != cudaSuccess) { if (out[0]) cudaFreeHost(out[0]); out[0] = out[1] = nullptr; return fail_cuda("pinned bounce ring", e); }
     }
-    out[0] = g_bounce[0]; out[1] = g_bounce[1];
-    g_bounce_busy = true;
     return 0;
 }
 
-void release_bounce(char* (&ring)[2], size_t) {
+void release_bounce(char* (&ring)[2], size_t bytes) {
+    if (!ring[0]) return;
     std::lock_guard<std::mutex> lk(g_bounce_mu);
-    if (ring[0] == g_bounce[0]) { g_bounce_busy = false; return; }
-    for (int k = 0; k < 2; ++k) if (ring[k]) cudaFreeHost(ring[k]);
+    g_bounce_free.push_back(BounceRing{{ring[0], ring[1]}, bytes});
+    ring[0] = ring[1] = nullptr;
 }
 
 // Dense host rows -> pitched device rows.  A pinned source goes in one 2-D copy; a pageable one (a std::vector) is
@@ -357,7 +365,7 @@ cudaError_t upload_rows(void* dev, size_t dev_pitch, const void* host, size_t ro
         return cudaMemcpy2D(dev, dev_pitch, host, row_bytes, row_bytes, static_cast<size_t>(n_rows), cudaMemcpyHostToDevice);
     int64_t stage_rows = kBounceBytes / static_cast<int64_t>(row_bytes);
     if (stage_rows < 1) stage_rows = 1;
-    const size_t need = static_cast<size_t>(stage_rows) * row_bytes;
+    size_t need = static_cast<size_t>(stage_rows) * row_bytes;
     char* ring[2] = {nullptr, nullptr};
     if (acquire_bounce(need, ring)) return cudaErrorMemoryAllocation;
     cudaStream_t st = nullptr;
@@ -416,10 +424,8 @@ int auvi_trim(void) {
     g_staging_free.clear();
     {
         std::lock_guard<std::mutex> lk3(g_bounce_mu);
-        if (!g_bounce_busy) {
-            for (int k = 0; k < 2; ++k) { if (g_bounce[k]) cudaFreeHost(g_bounce[k]); g_bounce[k] = nullptr; }
-            g_bounce_bytes = 0;
-        }
+        for (BounceRing& r : g_bounce_free) { cudaFreeHost(r.buf[0]); cudaFreeHost(r.buf[1]); }
+        g_bounce_free.clear();
     }
     return 0;
 }
@@ -671,8 +677,9 @@ int auvi_lattice(auvi_grid* g, int method, int axis_kind, int f_lat, int f_lon, 
         g->d_rows_bytes = need;
     }
     char* bounce[2] = {nullptr, nullptr};
+    size_t bounce_bytes = need;
     if (pageable) {
-        if (acquire_bounce(need, bounce)) return 2;
+        if (acquire_bounce(bounce_bytes, bounce)) return 2;
     }
     float ms_total = 0.f;
     int64_t c = 0;
@@ -710,7 +717,7 @@ int auvi_lattice(auvi_grid* g, int method, int axis_kind, int f_lat, int f_lon, 
     }
     for (int64_t k = (c >= 2 ? c - 2 : 0); k < c && !rc; ++k) rc = drain(static_cast<int>(k & 1));
     if (rc) quiesce(g);
-    if (pageable) { cudaDeviceSynchronize(); release_bounce(bounce, need); }
+    if (pageable) { cudaDeviceSynchronize(); release_bounce(bounce, bounce_bytes); }
     g->last_ms = ms_total;
     return rc;
 }

@@ -309,12 +309,12 @@ __device__ __forceinline__ bool near_query(S& s, const FillParams<T>& p, const T
     return true;
 }
 
-template <typename T, int METHOD, bool FILL, int THREADS, int STAGES>
+template <typename T, int METHOD, bool FILL, int THREADS, int STAGES, bool PATCH>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 2)
 fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FillParams<T> p) {
     using Smem = FillSmem<T, THREADS, STAGES>;
     // results go into the staged tile unless the method also READS masked cells of the tile (bilinear corners)
-    constexpr bool kPatch = FILL && METHOD != BILINEAR && METHOD != BILINEAR_SEARCH;
+    constexpr bool kPatch = PATCH && FILL && METHOD != BILINEAR && METHOD != BILINEAR_SEARCH;
     constexpr int kWarps = THREADS / 32;
     constexpr int kPer = (kFCells + THREADS - 1) / THREADS;        // queries per thread when every cell is masked
     constexpr uint32_t kBoxBytes = kFBW * kFBH * sizeof(T);
@@ -1071,7 +1071,7 @@ static cudaError_t fill_params(const GridDesc& d, const AxisTables& lat, const A
     return cudaSuccess;
 }
 
-template <typename T, int METHOD, bool FILL, int THREADS, int STAGES>
+template <typename T, int METHOD, bool FILL, int THREADS, int STAGES, bool PATCH = true>
 static cudaError_t launch_fill_cfg(const GridDesc& d, const AxisTables& lat, const AxisTables& lon, int64_t row_begin,
                                    int64_t row_end, void* out, int64_t out_ld, cudaStream_t st, LaunchInfo* info) {
     FillParams<T> p;
@@ -1080,12 +1080,13 @@ static cudaError_t launch_fill_cfg(const GridDesc& d, const AxisTables& lat, con
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
     p.use_tma = make_grid_tensor_map(d, kFBW, kFBH, &tmap, /*nan_fill=*/true) ? 1 : 0;
-    auto kern = fill_tiled_kernel<T, METHOD, FILL, THREADS, STAGES>;
+    auto kern = fill_tiled_kernel<T, METHOD, FILL, THREADS, STAGES, PATCH>;
     const size_t smem = sizeof(FillSmem<T, THREADS, STAGES>);
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     static const int slots = resident_ctas(kern, THREADS, smem);  // per instantiation; every device of a box is alike
-    const int grid = p.n_tiles < slots ? p.n_tiles : slots;
+    static const bool one_tile_per_cta = getenv("AUVI_FILL_ONE_TILE") != nullptr;   // A/B: the non-persistent launch shape
+    const int grid = (p.n_tiles < slots || one_tile_per_cta) ? p.n_tiles : slots;
     kern<<<grid, THREADS, smem, st>>>(tmap, p);
     if (info) { info->launches += 1; info->used_tma = p.use_tma; }
     return cudaGetLastError();
@@ -1128,6 +1129,10 @@ static cudaError_t launch_fill_t(const GridDesc& d, const AxisTables& lat, const
     } else {
         static const int cfg = [] { const char* e = getenv("AUVI_FILL_CFG"); return e ? atoi(e) : 0; }();
         if (cfg == 1) return launch_fill_cfg<T, METHOD, FILL, 256, 1>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
+        if constexpr (METHOD == IDW && FILL && sizeof(T) == 4) {   // A/B only: results stored per query instead of patched
+            if (cfg == 2) return launch_fill_cfg<T, METHOD, FILL, 256, 1, false>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
+            if (cfg == 3) return launch_fill_cfg<T, METHOD, FILL, 384, 2, false>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
+        }
         return launch_fill_cfg<T, METHOD, FILL, 384, sizeof(T) == 4 ? 2 : 1>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
     }
 }

@@ -12,8 +12,12 @@
 //   * synchronous calls, one host thread.
 // What changed: the grid upload happens once and stays resident; per-call buffers are persistent
 // pinned/device staging inside libauvi, and copies overlap kernels chunk by chunk.
+// AUVI_GPUS=n (environment, n > 1): the grid is replicated on n devices and every batch is cut into one slice per
+// device (auvi_multi_*); the class layout cannot grow (the drivers are compiled against the reference's header), so
+// the multi-device handle is told apart from the single-device one by bit 0 of the stored pointer.
 #include "include/GridD.h"
 
+#include <cstdint>
 #include <cstdlib>
 #include <iostream>
 
@@ -26,15 +30,26 @@ namespace {
     std::exit(1);
 }
 
+inline bool is_multi(const double* p) { return (reinterpret_cast<uintptr_t>(p) & 1u) != 0; }
 inline auvi_grid* handle(double* p) { return reinterpret_cast<auvi_grid*>(p); }
+inline auvi_multi* multi_handle(double* p) { return reinterpret_cast<auvi_multi*>(reinterpret_cast<uintptr_t>(p) & ~uintptr_t(1)); }
+
+int gpus_wanted() {
+    const char* e = std::getenv("AUVI_GPUS");
+    const int n = e ? std::atoi(e) : 1;
+    const int have = auvi_device_count();
+    return n < 1 ? 1 : (n > have && have > 0 ? have : n);
+}
 
 std::vector<Point> run_batch(double* d_grid, bool initialized, int method, const std::vector<Point>& query_points,
                              const char* where) {
     if (!initialized || query_points.empty()) return query_points;
     std::vector<Point> results = query_points;
-    if (auvi_interp_points(handle(d_grid), method, query_points.data(), static_cast<int64_t>(query_points.size()),
-                           sizeof(Point), &results[0].elev, sizeof(Point)) != 0)
-        die(where);
+    const int64_t n = static_cast<int64_t>(query_points.size());
+    const int rc = is_multi(d_grid)
+        ? auvi_multi_interp_points(multi_handle(d_grid), method, query_points.data(), n, sizeof(Point), &results[0].elev, sizeof(Point))
+        : auvi_interp_points(handle(d_grid), method, query_points.data(), n, sizeof(Point), &results[0].elev, sizeof(Point));
+    if (rc != 0) die(where);
     return results;
 }
 
@@ -58,16 +73,25 @@ void GridD::initialize(const std::vector<std::vector<double>>& elevation_data) {
     std::vector<double> dense(static_cast<size_t>(num_lat) * num_lon);
     for (int j = 0; j < num_lat; ++j)
         for (int i = 0; i < num_lon; ++i) dense[static_cast<size_t>(j) * num_lon + i] = elevation_data[j][i];
-    auvi_grid* g = nullptr;
-    if (auvi_grid_create(dense.data(), AUVI_F64, num_lat, num_lon, min_lon, max_lon, min_lat, max_lat, 0, &g) != 0)
-        die("GridD::initialize");
-    d_grid = reinterpret_cast<double*>(g);
+    const int n_gpus = gpus_wanted();
+    if (n_gpus > 1) {
+        auvi_multi* m = nullptr;
+        if (auvi_multi_create(dense.data(), AUVI_F64, num_lat, num_lon, min_lon, max_lon, min_lat, max_lat, n_gpus, nullptr,
+                              /*replicate=*/1, &m) != 0)
+            die("GridD::initialize");
+        d_grid = reinterpret_cast<double*>(reinterpret_cast<uintptr_t>(m) | 1u);
+    } else {
+        auvi_grid* g = nullptr;
+        if (auvi_grid_create(dense.data(), AUVI_F64, num_lat, num_lon, min_lon, max_lon, min_lat, max_lat, 0, &g) != 0)
+            die("GridD::initialize");
+        d_grid = reinterpret_cast<double*>(g);
+    }
     initialized = true;
 }
 
 void GridD::cleanup() {
     if (initialized && d_grid != nullptr) {
-        if (auvi_grid_destroy(handle(d_grid)) != 0) die("GridD::cleanup");
+        if ((is_multi(d_grid) ? auvi_multi_destroy(multi_handle(d_grid)) : auvi_grid_destroy(handle(d_grid))) != 0) die("GridD::cleanup");
         d_grid = nullptr;
         initialized = false;
     }

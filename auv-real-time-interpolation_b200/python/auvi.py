@@ -56,6 +56,17 @@ SYMBOLS = {
     "auvi_peer_export": (_i32, [_vp, _vp]),
     "auvi_peer_open": (_i32, [_vp, C.POINTER(_vp)]),
     "auvi_peer_close": (_i32, [_vp]),
+    "auvi_multi_create": (_i32, [_vp, _i32, _i64, _i64, _dbl, _dbl, _dbl, _dbl, _i32, _vp, _i32, C.POINTER(_vp)]),
+    "auvi_multi_destroy": (_i32, [_vp]),
+    "auvi_multi_count": (_i32, [_vp]),
+    "auvi_multi_shard": (_i32, [_vp, _i32, _i32, C.POINTER(_i32), C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),
+    "auvi_multi_mask_hash": (_i32, [_vp, _dbl, C.c_uint64]),
+    "auvi_multi_lattice": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "auvi_multi_lattice_device": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64]),
+    "auvi_multi_enable_peer": (_i32, [_vp, _i32]),
+    "auvi_multi_sync": (_i32, [_vp]),
+    "auvi_multi_last_kernel_ms": (C.c_float, [_vp]),
+    "auvi_multi_interp_points": (_i32, [_vp, _i32, _vp, _i64, _i64, _vp, _i64]),
     "auvi_last_error": (C.c_char_p, []),
     "auvi_last_kernel_ms": (C.c_float, [_vp]),
     "auvi_launch_count": (_i64, []),
@@ -276,3 +287,69 @@ def error_metrics_device(truth_ptr, est_ptr, dtype, n, stream=None):
     nn = _i64()
     _check(load().auvi_error_metrics_device(truth_ptr, est_ptr, dtype, n, out3, C.byref(nn), stream))
     return out3[0], out3[1], out3[2], nn.value
+
+
+class MultiGrid:
+    """One host grid on several GPUs of this process (auvi_multi_*): row slabs + halo, or replicated."""
+
+    def __init__(self, z, min_lon, max_lon, min_lat, max_lat, n_gpus, devices=None, replicate=False, dtype=None):
+        lib = load()
+        if dtype is None:
+            dtype = F32 if np.asarray(z).dtype == np.float32 else F64
+        self.dtype = dtype
+        z = np.ascontiguousarray(z, dtype=_np_dtype(dtype))
+        self.n_lat, self.n_lon = z.shape
+        self._h = _vp()
+        dev = (C.c_int * n_gpus)(*devices) if devices is not None else None
+        _check(lib.auvi_multi_create(z.ctypes.data, dtype, self.n_lat, self.n_lon, min_lon, max_lon, min_lat, max_lat,
+                                     n_gpus, dev, 1 if replicate else 0, C.byref(self._h)))
+        self.n = n_gpus
+
+    def close(self):
+        if self._h:
+            load().auvi_multi_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def shard(self, k, f_lat=1):
+        """-> (device, row_lo, row_hi) of shard k at lattice factor f_lat."""
+        dev, lo, hi, g = _i32(), _i64(), _i64(), _vp()
+        _check(load().auvi_multi_shard(self._h, k, f_lat, C.byref(dev), C.byref(g), C.byref(lo), C.byref(hi)))
+        return dev.value, lo.value, hi.value
+
+    def mask_hash(self, fraction, seed=42):
+        _check(load().auvi_multi_mask_hash(self._h, fraction, seed))
+
+    def lattice(self, method, axis_kind, f_lat=1, f_lon=1, fill=0, out=None):
+        rows = f_lat * (self.n_lat - 1) + 1
+        cols = f_lon * (self.n_lon - 1) + 1
+        if out is None:
+            out = np.empty((rows, cols), dtype=_np_dtype(self.dtype))
+        _check(load().auvi_multi_lattice(self._h, method, axis_kind, f_lat, f_lon, fill, out.ctypes.data))
+        return out
+
+    def lattice_device(self, method, axis_kind, f_lat, f_lon, fill, out_ptrs, out_ld):
+        arr = (_vp * self.n)(*out_ptrs)
+        _check(load().auvi_multi_lattice_device(self._h, method, axis_kind, f_lat, f_lon, fill, arr, out_ld))
+
+    def enable_peer(self, root_shard=0):
+        _check(load().auvi_multi_enable_peer(self._h, root_shard))
+
+    def sync(self):
+        _check(load().auvi_multi_sync(self._h))
+
+    @property
+    def last_kernel_ms(self):
+        return float(load().auvi_multi_last_kernel_ms(self._h))
+
+    def interp_points(self, method, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        out = np.empty(pts.shape[0], dtype=np.float64)
+        _check(load().auvi_multi_interp_points(self._h, method, pts.ctypes.data, pts.shape[0], pts.strides[0],
+                                               out.ctypes.data, 8))
+        return out

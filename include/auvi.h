@@ -174,6 +174,38 @@ int auvi_peer_export(const void* dev_ptr, unsigned char* handle72);
 int auvi_peer_open(const unsigned char* handle72, void** out_ptr);     /* in another process of the same node */
 int auvi_peer_close(void* ptr);                                        /* a pointer returned by auvi_peer_open */
 
+/* ---- Several GPUs of one box, ONE process (the reference has no multi-GPU path: GridD owns one device grid,
+ *      src/GridD.cu:41-83, and every batch runs on it, :95-236).  Every output cell is independent, so the work shards
+ *      with no data-path collective: lattice / gap-fill jobs by blocks of grid rows -- shard k holds
+ *      its rows + a 14-row halo, replicated at upload, never exchanged -- and point lists by slices of the query list
+ *      over a replicated grid.  One host thread per device drives the single-GPU entries above. ------------------- */
+typedef struct auvi_multi auvi_multi;
+
+/* Upload one dense host grid to n_gpus devices (devices: CUDA ordinals, NULL = 0..n_gpus-1; an ordinal may repeat).
+ * replicate = 0: row slabs + halo (lattice / gap fill; what BASELINE config 4 needs at 65536^2);
+ * replicate = 1: every device holds the whole grid (also serves point lists: GridD::batch*). */
+int auvi_multi_create(const void* host_rowmajor, int dtype, int64_t n_lat, int64_t n_lon, double min_lon, double max_lon,
+                      double min_lat, double max_lat, int n_gpus, const int* devices, int replicate, auvi_multi** out);
+int auvi_multi_destroy(auvi_multi* m);
+int auvi_multi_count(const auvi_multi* m);
+/* Shard k: its device, its single-GPU handle (borrowed) and the lattice rows [row_lo,row_hi) it produces at factor f_lat. */
+int auvi_multi_shard(const auvi_multi* m, int k, int f_lat, int* device, auvi_grid** grid, int64_t* row_lo, int64_t* row_hi);
+/* auvi_grid_mask_hash on every shard: one global mask, no communication. */
+int auvi_multi_mask_hash(auvi_multi* m, double fraction, uint64_t seed);
+/* auvi_lattice over all devices at once; host_out is the whole lattice (rows x cols, dense).  Synchronous. */
+int auvi_multi_lattice(auvi_multi* m, int method, int axis_kind, int f_lat, int f_lon, int fill, void* host_out);
+/* Device-resident form, asynchronous: dev_out[k] = where shard k's kernel writes the FIRST of its rows (pitch out_ld
+ * elements).  Separate buffers leave the result sharded; addresses inside one buffer on one device (after
+ * auvi_multi_enable_peer) gather it there -- the kernels' own stores cross NVLink, compute and gather are one kernel. */
+int auvi_multi_lattice_device(auvi_multi* m, int method, int axis_kind, int f_lat, int f_lon, int fill, void* const* dev_out,
+                              int64_t out_ld);
+int auvi_multi_enable_peer(auvi_multi* m, int root_shard);   /* every shard's device may store to root_shard's device */
+int auvi_multi_sync(auvi_multi* m);                          /* waits for every device */
+float auvi_multi_last_kernel_ms(const auvi_multi* m);        /* device time of the last job, max over the devices */
+/* auvi_interp_points with the query list cut into one slice per device (needs replicate = 1). */
+int auvi_multi_interp_points(auvi_multi* m, int method, const void* host_pts, int64_t n, int64_t stride_bytes, void* host_out,
+                             int64_t out_stride_bytes);
+
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 const char* auvi_last_error(void);          /* thread-local message of the last failure */
 float auvi_last_kernel_ms(const auvi_grid* g); /* device time of the kernels of the last synchronous call */

@@ -34,8 +34,10 @@ def _write_matrix_csv(fn, z):
             f.write(",".join("nan" if np.isnan(v) else repr(float(v)) for v in row) + "\n")
 
 
-@pytest.mark.parametrize("tile,frac", [("mid_atlantic", 0.10), ("mariana", 0.50)])   # the second is BASELINE configs[1] verbatim
-def test_test_gebco_runs_unchanged(tmp_path, tile, frac):
+# the second case is BASELINE configs[1] verbatim; the third runs GridD over two devices (AUVI_GPUS: the grid replicated, the
+# batch cut into one slice per device -- on a one-GPU box GridD clamps to the devices it has)
+@pytest.mark.parametrize("tile,frac,gpus", [("mid_atlantic", 0.10, None), ("mariana", 0.50, None), ("mariana", 0.50, "2")])
+def test_test_gebco_runs_unchanged(tmp_path, tile, frac, gpus):
     from oracle import binding as ob
     exe = _need("test_gebco")
     case = ob.masked_case(tile, frac)
@@ -48,7 +50,10 @@ def test_test_gebco_runs_unchanged(tmp_path, tile, frac):
         f.write("row,col,ref_elev\n")
         for r, c, t in zip(case["rows"], case["cols"], case["truth"]):
             f.write(f"{r},{c},{t}\n")
-    out = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ)
+    if gpus:
+        env["AUVI_GPUS"] = gpus
+    out = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "Wrote the following to csv: GPU Kriging" in out.stdout
     rows = list(csv.reader(open(res / "TestingResults1.csv")))
