@@ -4,25 +4,18 @@
 // through.  This is the structured form of the reference's Grid-B procedure (test_gebco.cpp:150-196: one query per
 // removed cell, built by gridIndexToGeo :72-81, evaluated by GridH::batch*Interpolate, GridH.cpp:160-420) and of
 // BASELINE config 4 (IDW / nearest-neighbour on a 70 % masked grid).  Methods: BILINEAR (four corners, NaN-corner mean:
-// no search; it has a kernel of its own below), CUBIC (always the ring-search 4-nearest mean here: a masked cell is
-// inside its own 4x4 stencil), KRIGING, NN, IDW, and the opt-in BILINEAR_SEARCH.
+// no search; inside this kernel only as the first stage of BILINEAR_SEARCH), CUBIC (always the ring-search 4-nearest mean here: a masked cell is inside its own 4x4 stencil), KRIGING,
+// NN, IDW, and the opt-in BILINEAR_SEARCH.
 // FILL = false: KRIGING / NN / IDW on an upsampling lattice (test_interpolation.cpp:283-297): every output cell a query.
 //
-// Design (v5, round 2; DESIGN.md section 5.3 has the numbers).  PERSISTENT CTAs: the grid is one CTA per resident slot
-// (SMs x CTAs per SM), each loops over 64 x 32 tiles of output cells, tile t+gridDim of the row-major tile order next.
-//   0. Once per CTA: the two lookup tables of the near path, the mbarriers.
+// Design (one CTA = 256 threads = one 64 x 32 tile of output cells; DESIGN.md section 5.3 has the numbers):
 //   1. The tile's grid cells + a 12-cell halo (88 x 56: search radius 10 + a centre that FP64 noise may move by one
-//      cell) are staged into shared memory by ONE TMA 2-D box load whose out-of-bounds cells arrive as NaN (so "outside
-//      the grid / outside the resident slab" and "masked" are the same thing downstream).  With STAGES = 2 the box of
-//      the NEXT tile is requested before this tile's work starts and lands in the other buffer while this tile is
-//      searched; with STAGES = 1 (FP64 grids: two 39 KB buffers do not fit) the next box is prefetched into L2.
-//      Meanwhile per-axis tables (index-space position, search centre, squared offsets of the near rings in the
-//      reference's operation order).
-//   2. Validity bitmasks (one 96-bit row per block row) from 16-byte shared-memory loads: a lane tests 4 (FP32) or 2
-//      (FP64) cells, 8 / 16 lanes OR their bits together with shuffles.  From here on the ring search of
-//      GridH.cpp:24-118 is bit arithmetic.
-//   3. A warp takes whole tile rows: masked cells are COMPACTED into a CTA-wide queue (popcounts of the warp-uniform
-//      row words, one shared atomic per row).
+//      cell) are staged into shared memory by ONE TMA 2-D box load; meanwhile per-axis tables (index-space position,
+//      search centre, squared offsets of the near rings in the reference's operation order) and two small LUTs.
+//   2. Warps turn the block into validity bitmasks with __ballot_sync (one 96-bit row per block row); from here on the
+//      ring search of GridH.cpp:24-118 is bit arithmetic.
+//   3. A warp takes whole tile rows: valid cells go straight to the output, masked cells are COMPACTED into a CTA-wide
+//      queue (popcounts of the warp-uniform row words, one shared atomic per row).
 //   4. Phase A1, one thread per query: the 5 x 5 block around the centre as ONE word whose bit order is the reference's
 //      enumeration order; four popcounts give the pass at which the reference stops, a mask gives its candidates.
 //      Searches that end inside the block with <= 8 candidates take the near path; the others get the general
@@ -36,12 +29,17 @@
 //      literal per-query path (exact.cuh).
 //   7. Epilogue on the four picks: mean / first pick / FP32 IDW weights through the SFU reciprocal / kriging (its FP64
 //      solve runs as a phase of its own over the recorded picks).
-//   8. FILL: every result is PATCHED INTO THE STAGED TILE (a masked cell is never read by a search -- candidates are
-//      valid cells), and the finished 64 x 32 tile leaves with 16-byte coalesced streaming stores: pass-through and
-//      results in one sweep, full 32-byte sectors, no per-query global store.
 //
-// Algorithmic HBM bytes: sizeof(T) read + sizeof(T) written per cell; the search methods are issue-bound
-// (integer / bit work + FP64 distance compares), not HBM-bound; bilinear_fill_kernel is HBM-bound.
+// Algorithmic HBM bytes: sizeof(T) read + sizeof(T) written per cell; the kernel is issue-bound (integer /
+// bit work + FP64 distance compares), not HBM-bound.
+//
+// BILINEAR gap fill has a kernel of its own at the end of this file (bilinear_fill_kernel: persistent CTAs, two-deep TMA
+// ring, 16-byte stores) -- it needs no search and is HBM-bound.  The same restructuring of THIS kernel (round 2, "v5":
+// persistent CTAs, two-deep TMA ring, vectorised bitmasks, results patched into the staged tile and stored as whole rows)
+// was built, parity-checked and measured on the same box against this form: it lost 6-13 % at every mask fraction
+// (profiles/r02_fill_v5_ab.txt), because the kernel is bound by issue slots and kernel text, not by
+// the TMA latency three resident CTAs per SM already hide.  Out-of-bounds cells of the staged block arrive as NaN (TMA
+// fill mode), so "outside the grid / outside the resident slab" and "masked" are one test.
 #include <cstdlib>
 #include <cstring>
 
@@ -55,7 +53,9 @@ constexpr int kFW = 64, kFH = 32;              // tile of output cells
 constexpr int kFHalo = 12;
 constexpr int kFBW = kFW + 2 * kFHalo;         // 88
 constexpr int kFBH = kFH + 2 * kFHalo;         // 56
+constexpr int kFThreads = 256;
 constexpr int kFCells = kFW * kFH;
+constexpr int kFPer = kFCells / kFThreads;     // queries per thread when every cell is masked
 constexpr int kFNMax = 13;                     // per-thread candidate list capacity of the general path (3 + a full ring-2 row pass)
 constexpr int kFRedoMax = 128;
 constexpr int kFReplayMax = 256;                // near-tie queries replayed with square roots (more: literal path)
@@ -98,19 +98,18 @@ struct FillParams {
     int n_out_cols;                           // lattice columns (== g.n_lon on the node lattice)
     int f_lat, f_lon;                         // integer upsampling factors of the lattice axes (1 on the node lattice)
     int use_tma;
-    int tiles_x, n_tiles;                     // tiles per tile row, tiles in all (row-major tile order)
-    int vec_ok;                               // out / out_ld allow 16-byte stores of tile rows
+    int tiles_x, n_tiles;                     // bilinear_fill_kernel: tiles per tile row, tiles in all (row-major order)
+    int vec_ok;                               // bilinear_fill_kernel: out / out_ld allow 16-byte stores
 };
 
-template <typename T, int THREADS, int STAGES>
+template <typename T>
 struct FillSmem {
-    alignas(128) T tile[STAGES][kFBH * kFBW];
-    double d2[kFNMax * THREADS];              // general path: per-thread candidate lists, squared distances.  Before the
+    alignas(128) T tile[kFBH * kFBW];
+    double d2[kFNMax * kFThreads];            // general path: per-thread candidate lists, squared distances.  Before the
                                               // general path runs, its first 8 KB hold two queues (see the kernel)
     double sqx[kFW * (2 * kFSq + 1)];         // ((cx + d + 0.5) - x)^2 per tile column, d = -kFSq..kFSq
     double sqy[kFH * (2 * kFSq + 1)];
     double x[kFW], y[kFH];
-    uint64_t bar[STAGES];
     uint32_t rec[kFCells];                    // query records, ordered by bin after the scatter
     uint32_t mask[kFBH * 4];
     uint32_t lut[5 * 32];                     // 5-bit row window of block row dy+2 -> its bits in enumeration order
@@ -119,30 +118,16 @@ struct FillSmem {
     int cell_dxy[32];                         // enumeration position -> (dx & 0xffff) | dy << 16
     int cx[kFW], cy[kFH];
     int hist[kFBins];
-    uint16_t code[kFNMax * THREADS];          // general path: per-thread candidate lists, packed (dy,dx) offsets
+    uint16_t code[kFNMax * kFThreads];        // general path: per-thread candidate lists, packed (dy,dx) offsets
     uint16_t reck[kFCells];                   // cell (lj*kFW + li) of each record
     uint16_t redo[kFRedoMax];
     uint16_t replay[kFReplayMax];
     int qn, rn, dn, tn, q_near, next;
+    uint64_t bar;
 };
 
-static_assert(sizeof(FillSmem<float, 256, 1>) <= 75 * 1024, "three CTAs per SM need <= 75 KB each");
-static_assert(sizeof(FillSmem<float, 384, 2>) <= 113 * 1024, "two CTAs per SM need <= 113 KB each");
-static_assert(sizeof(FillSmem<double, 384, 1>) <= 113 * 1024, "two CTAs per SM (f64 grids)");
-static_assert(sizeof(FillSmem<double, 256, 1>) <= 113 * 1024, "two CTAs per SM (f64 grids)");
-
-// Where a result goes.  PATCH: into the staged tile in shared memory (core = its cell (0,0)); the whole tile is stored
-// afterwards.  Else: straight to the output with a streaming store.
-template <typename T, bool PATCH>
-struct Emit {
-    T* core;
-    T* out_tile;
-    int64_t out_ld;
-    __device__ __forceinline__ void operator()(int lj, int li, T v) const {
-        if (PATCH) core[lj * kFBW + li] = v;
-        else __stcs(out_tile + lj * out_ld + li, v);
-    }
-};
+static_assert(sizeof(FillSmem<float>) <= 75 * 1024, "three CTAs per SM need <= 75 KB each (f32 grids)");
+static_assert(sizeof(FillSmem<double>) <= 113 * 1024, "two CTAs per SM (f64 grids)");
 
 template <typename T, int METHOD>
 __device__ __noinline__ T fill_cell_literal(const FillParams<T>* p, int64_t J, int I) {
@@ -253,9 +238,9 @@ __device__ __noinline__ T finish_few(int cnt, double v0, double v1, double v2, d
 // so a pass can only come out differently if a remaining value lies above the pass minimum by less than sqrt
 // rounding can close.  That is checked on the sorted chain afterwards; such a query returns false and is replayed
 // with REPLAY = true, which takes the square roots first -- the reference's own comparison, bit for bit.
-template <typename T, int METHOD, int N, bool REPLAY, typename S, typename E>
-__device__ __forceinline__ bool near_query(S& s, const FillParams<T>& p, const T* tl, const E& emit, uint32_t cand, int q, int k,
-                                           int c0, int r0, int I0, int64_t J0) {
+template <typename T, int METHOD, int N, bool REPLAY>
+__device__ __forceinline__ bool near_query(FillSmem<T>& s, const FillParams<T>& p, uint32_t cand, int q, int k, int c0,
+                                           int r0, int I0, int64_t J0, T* out_tile) {
     constexpr int kPasses = METHOD == NN ? 1 : 4;
     const int lj = k / kFW, li = k % kFW;
     const char* const sqx = reinterpret_cast<const char*>(s.sqx + li * (2 * kFSq + 1) + kFSq - 2);   // [dx + 2]
@@ -293,7 +278,7 @@ __device__ __forceinline__ bool near_query(S& s, const FillParams<T>& p, const T
         return true;
     }
     const int cig = s.cx[li], cjg = s.cy[lj];
-    const T* const centre = tl + (cjg - r0) * kFBW + (cig - c0);
+    const T* const centre = s.tile + (cjg - r0) * kFBW + (cig - c0);
     T v[4];
     double d2[4];
     const int pi[4] = {0, 0, 0, 0}, pj[4] = {0, 0, 0, 0};
@@ -305,27 +290,30 @@ __device__ __forceinline__ bool near_query(S& s, const FillParams<T>& p, const T
             d2[e] = dadd(*reinterpret_cast<const double*>(sqx + (off & 0xffffu)), *reinterpret_cast<const double*>(sqy + (off >> 16)));
         } else d2[e] = d[e];
     }
-    emit(lj, li, finish_four<T, METHOD>(p, v, d2, pi, pj, I0 + li, J0 + lj));
+    __stcs(out_tile + lj * p.out_ld + li, finish_four<T, METHOD>(p, v, d2, pi, pj, I0 + li, J0 + lj));
     return true;
 }
 
-template <typename T, int METHOD, bool FILL, int THREADS, int STAGES, bool PATCH>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 2)
+template <typename T, int METHOD, bool FILL>
+__global__ void __launch_bounds__(kFThreads, 3)
 fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FillParams<T> p) {
-    using Smem = FillSmem<T, THREADS, STAGES>;
-    // results go into the staged tile unless the method also READS masked cells of the tile (bilinear corners)
-    constexpr bool kPatch = PATCH && FILL && METHOD != BILINEAR && METHOD != BILINEAR_SEARCH;
-    constexpr int kWarps = THREADS / 32;
-    constexpr int kPer = (kFCells + THREADS - 1) / THREADS;        // queries per thread when every cell is masked
-    constexpr uint32_t kBoxBytes = kFBW * kFBH * sizeof(T);
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    FillSmem<T>& s = *reinterpret_cast<FillSmem<T>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = p.g.n_lon;                                       // grid columns; the lattice has p.n_out_cols
+    const int I0 = blockIdx.x * kFW;
+    const int64_t J0 = p.row_begin + static_cast<int64_t>(blockIdx.y) * kFH;
+    // first grid column / row of the staged block: the tile's first node minus the halo, the column rounded down to a
+    // 16-byte boundary for TMA (on the node lattice I0 - 12 already is one)
+    const int c0 = (I0 / p.f_lon - kFHalo) & ~3;
+    const int r0 = static_cast<int>(J0 / p.f_lat) - kFHalo;
+    T* const out_tile = p.out + (J0 - p.row_begin) * p.out_ld + I0;
     // two queues live in the general path's list storage until that path starts:
     uint16_t* const queue = reinterpret_cast<uint16_t*>(s.d2);     // masked cells of the tile, compacted (read by phase A1)
     uint16_t* const defer = queue + kFCells;                       // A1 -> A2: queries the 5 x 5 block cannot decide
 
-    // ---- once per CTA: lookup tables of the near path, barriers ---------------------------------------------------------
+    if (tid == 0) { s.qn = 0; s.rn = 0; s.dn = 0; s.tn = 0; s.next = 0; }
+    if (tid < kFBins) s.hist[tid] = 0;
     if (tid < 5 * 32) {
         const int dy = tid / 32 - 2, w = tid & 31;
         uint32_t v = 0;
@@ -340,424 +328,338 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         s.cell_tile[pos] = dy * kFBW + dx;
         s.cell_dxy[pos] = (dx & 0xffff) | (dy << 16);
     }
-    for (int r = tid; r < kFBH; r += THREADS) s.mask[r * 4 + 3] = 0u;   // the fourth word of a mask row stays empty
-    if (p.use_tma && tid == 0) {
-        prefetch_tmap(&tmap);
+    if (p.use_tma) {
+        if (tid == 0) { prefetch_tmap(&tmap); mbar_init(&s.bar, 1); }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&s.bar, static_cast<uint32_t>(kFBW * kFBH * sizeof(T)));
+            tma_load_2d(s.tile, &tmap, c0, r0 - p.g.row0, &s.bar);
+        }
+    } else {
+        for (int k = tid; k < kFBW * kFBH; k += kFThreads) {
+            const int lr = k / kFBW, lc = k - lr * kFBW;
+            const int gr = r0 + lr, gc = c0 + lc;
+            T v = static_cast<T>(qnan());
+            if (gr >= p.rows_resident_lo && gr < p.rows_resident_hi && gc >= 0 && gc < W)
+                v = __ldg(p.g.z + static_cast<int64_t>(gr - p.g.row0) * p.g.ld + gc);
+            s.tile[k] = v;
+        }
+    }
+    // per-axis query tables of this tile (overlaps the TMA flight): index-space position, search centre and
+    // the squared offsets of the near rings
+    if (tid < kFW) {
+        const int I = I0 + tid;
+        double x = qnan();
+        int c = 0;
+        if (I < p.n_out_cols) {
+            x = __ldg(p.lon.pos + I);
+            c = (METHOD == CUBIC || METHOD == BILINEAR || METHOD == BILINEAR_SEARCH) ? __ldg(p.lon.base + I) : (isnan(x) ? 0 : round_centre(x, p.g.n_lon));
+        }
+        s.x[tid] = x; s.cx[tid] = c;
+        const double cf = dadd(__int2double_rn(c), 0.5);
 #pragma unroll
-        for (int b = 0; b < STAGES; ++b) mbar_init(&s.bar[b], 1);
+        for (int d = -kFSq; d <= kFSq; ++d) s.sqx[tid * (2 * kFSq + 1) + d + kFSq] = sq_offset(cf, d, x);
+    } else if (tid < kFW + kFH) {
+        const int t = tid - kFW;
+        const int64_t J = J0 + t;
+        double y = qnan();
+        int c = 0;
+        if (J < p.row_end) {
+            y = __ldg(p.lat.pos + J);
+            c = (METHOD == CUBIC || METHOD == BILINEAR || METHOD == BILINEAR_SEARCH) ? __ldg(p.lat.base + J) : (isnan(y) ? 0 : round_centre(y, p.g.n_lat));
+        }
+        s.y[t] = y; s.cy[t] = c;
+        const double cf = dadd(__int2double_rn(c), 0.5);
+#pragma unroll
+        for (int d = -kFSq; d <= kFSq; ++d) s.sqy[t * (2 * kFSq + 1) + d + kFSq] = sq_offset(cf, d, y);
+    }
+    if (p.use_tma) mbar_wait(&s.bar, 0);
+    else __syncthreads();
+
+    // ---- validity bitmasks: bit c of row r = tile cell (r,c) holds a number and lies inside the grid ----
+    // (cells outside the grid or outside the resident slab arrive as NaN: the TMA map fills them so, the plain loader
+    // writes them so)
+    for (int r = warp; r < kFBH; r += kFThreads / 32) {
+#pragma unroll
+        for (int seg = 0; seg < 3; ++seg) {
+            const int c = seg * 32 + lane;
+            bool ok = false;
+            if (c < kFBW) ok = !isnan(s.tile[r * kFBW + c]);
+            const uint32_t word = __ballot_sync(0xffffffffu, ok);
+            if (lane == 0) s.mask[r * 4 + seg] = word;
+        }
+        if (lane == 0) s.mask[r * 4 + 3] = 0u;
     }
     __syncthreads();
 
-    // first grid column / row of the staged block of tile t: the tile's first node minus the halo, the column rounded
-    // down to a 16-byte boundary for TMA (on the node lattice I0 - 12 already is one)
-    auto tile_origin = [&](int t, int& I0, int64_t& J0, int& c0, int& r0) {
-        const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
-        I0 = tx * kFW;
-        J0 = p.row_begin + static_cast<int64_t>(ty) * kFH;
-        c0 = (I0 / p.f_lon - kFHalo) & ~3;
-        r0 = static_cast<int>(J0 / p.f_lat) - kFHalo;
-    };
-    auto request_tile = [&](int t, int b) {                        // one thread: box of tile t into buffer b
-        int I0, c0, r0; int64_t J0;
-        tile_origin(t, I0, J0, c0, r0);
-        mbar_expect_tx(&s.bar[b], kBoxBytes);
-        tma_load_2d(s.tile[b], &tmap, c0, r0 - p.g.row0, &s.bar[b]);
-    };
-    int tile = blockIdx.x;
-    if (p.use_tma && tid == 0 && tile < p.n_tiles) request_tile(tile, 0);
-
-    for (int it = 0; tile < p.n_tiles; ++it, tile += gridDim.x) {
-        const int buf = STAGES == 2 ? (it & 1) : 0;
-        const uint32_t parity = STAGES == 2 ? ((it >> 1) & 1) : (it & 1);
-        T* const tl = s.tile[buf];
-        int I0, c0, r0; int64_t J0;
-        tile_origin(tile, I0, J0, c0, r0);
-        const int W = p.g.n_lon;                                   // grid columns; the lattice has p.n_out_cols
-        T* const out_tile = p.out + (J0 - p.row_begin) * p.out_ld + I0;
-        const Emit<T, kPatch> emit{tl + kFHalo * kFBW + kFHalo, out_tile, p.out_ld};
-
-        if (tid == 0) { s.qn = 0; s.rn = 0; s.dn = 0; s.tn = 0; s.next = 0; }
-        if (tid < kFBins) s.hist[tid] = 0;
-        if (p.use_tma) {
-            const int nxt = tile + gridDim.x;
-            if (tid == 0 && nxt < p.n_tiles) {
-                if (STAGES == 2) request_tile(nxt, buf ^ 1);       // the other buffer was drained by the previous iteration
-                else {                                             // one buffer: at least bring the next box into L2
-                    int nI0, nc0, nr0; int64_t nJ0;
-                    tile_origin(nxt, nI0, nJ0, nc0, nr0);
-                    tma_prefetch_l2_2d(&tmap, nc0, nr0 - p.g.row0);
-                }
+    // ---- pass valid cells through (coalesced), compact masked cells into the queue -------------------------
+    // A warp takes whole tile rows: the row's validity is two words of the bitmask, the same for every lane, so the
+    // queue slots come from popcounts instead of ballots, one shared-memory atomic per row.
+    {
+        const int ncols = min(kFW, p.n_out_cols - I0);
+        const uint32_t range_lo = ncols >= 32 ? 0xffffffffu : (1u << ncols) - 1u;
+        const uint32_t range_hi = ncols >= 64 ? 0xffffffffu : (ncols > 32 ? (1u << (ncols - 32)) - 1u : 0u);
+        const uint32_t below = (1u << lane) - 1u;
+        for (int lj = warp; lj < kFH; lj += kFThreads / 32) {
+            if (J0 + lj >= p.row_end) break;
+            const uint32_t* const mrow = s.mask + (lj + kFHalo) * 4;
+            const uint32_t v_lo = __funnelshift_r(mrow[0], mrow[1], kFHalo), v_hi = __funnelshift_r(mrow[1], mrow[2], kFHalo);
+            const uint32_t todo_lo = FILL ? ~v_lo & range_lo : range_lo, todo_hi = FILL ? ~v_hi & range_hi : range_hi;
+            const int n_lo = __popc(todo_lo), n_row = n_lo + __popc(todo_hi);
+            int base = 0;
+            if (lane == 0 && n_row) base = atomicAdd(&s.qn, n_row);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const T* const trow = s.tile + (lj + kFHalo) * kFBW + kFHalo;
+            T* const orow = out_tile + lj * p.out_ld;
+            if (FILL) {
+                if ((v_lo & range_lo) >> lane & 1u) __stcs(orow + lane, trow[lane]);
+                if ((v_hi & range_hi) >> lane & 1u) __stcs(orow + 32 + lane, trow[32 + lane]);
             }
-        } else {
-            for (int k = tid; k < kFBW * kFBH; k += THREADS) {
-                const int lr = k / kFBW, lc = k - lr * kFBW;
-                const int gr = r0 + lr, gc = c0 + lc;
-                T v = static_cast<T>(qnan());
-                if (gr >= p.rows_resident_lo && gr < p.rows_resident_hi && gc >= 0 && gc < W)
-                    v = __ldg(p.g.z + static_cast<int64_t>(gr - p.g.row0) * p.g.ld + gc);
-                tl[k] = v;
-            }
+            if (todo_lo >> lane & 1u) queue[base + __popc(todo_lo & below)] = static_cast<uint16_t>(lj * kFW + lane);
+            if (todo_hi >> lane & 1u) queue[base + n_lo + __popc(todo_hi & below)] = static_cast<uint16_t>(lj * kFW + 32 + lane);
         }
-        // per-axis query tables of this tile (overlaps the TMA flight): index-space position, search centre and
-        // the squared offsets of the near rings
-        if (tid < kFW) {
-            const int I = I0 + tid;
-            double x = qnan();
-            int c = 0;
-            if (I < p.n_out_cols) {
-                x = __ldg(p.lon.pos + I);
-                c = (METHOD == CUBIC || METHOD == BILINEAR || METHOD == BILINEAR_SEARCH) ? __ldg(p.lon.base + I) : (isnan(x) ? 0 : round_centre(x, p.g.n_lon));
-            }
-            s.x[tid] = x; s.cx[tid] = c;
-            const double cf = dadd(__int2double_rn(c), 0.5);
-#pragma unroll
-            for (int d = -kFSq; d <= kFSq; ++d) s.sqx[tid * (2 * kFSq + 1) + d + kFSq] = sq_offset(cf, d, x);
-        } else if (tid < kFW + kFH) {
-            const int t = tid - kFW;
-            const int64_t J = J0 + t;
-            double y = qnan();
-            int c = 0;
-            if (J < p.row_end) {
-                y = __ldg(p.lat.pos + J);
-                c = (METHOD == CUBIC || METHOD == BILINEAR || METHOD == BILINEAR_SEARCH) ? __ldg(p.lat.base + J) : (isnan(y) ? 0 : round_centre(y, p.g.n_lat));
-            }
-            s.y[t] = y; s.cy[t] = c;
-            const double cf = dadd(__int2double_rn(c), 0.5);
-#pragma unroll
-            for (int d = -kFSq; d <= kFSq; ++d) s.sqy[t * (2 * kFSq + 1) + d + kFSq] = sq_offset(cf, d, y);
-        }
-        if (p.use_tma) mbar_wait(&s.bar[buf], parity);
-        else __syncthreads();
+    }
+    __syncthreads();
 
-        // ---- validity bitmasks: bit c of row r = block cell (r,c) holds a number (cells outside the grid or the resident
-        // slab arrived as NaN).  One 16-byte load per lane; the lanes of a word OR their bits together.
-        {
-            constexpr int VEC = 16 / static_cast<int>(sizeof(T));  // cells per lane: 4 (FP32), 2 (FP64)
-            constexpr int LPW = 32 / VEC;                          // lanes per 32-bit word
-            constexpr int SLOTS = 96 / VEC;                        // lane slots per block row (three words)
-            constexpr int REAL = kFBW / VEC;                       // slots that hold cells
-            static_assert((kFBH * SLOTS) % 32 == 0, "whole warps");
-            for (int k = tid; k < kFBH * SLOTS; k += THREADS) {    // warp-uniform bound
-                const int r = k / SLOTS, sl = k - r * SLOTS;
-                uint32_t bits = 0;
-                if (sl < REAL) {
-                    if constexpr (sizeof(T) == 4) {
-                        const float4 v = *reinterpret_cast<const float4*>(tl + r * kFBW + sl * VEC);
-                        bits = (v.x == v.x ? 1u : 0u) | (v.y == v.y ? 2u : 0u) | (v.z == v.z ? 4u : 0u) | (v.w == v.w ? 8u : 0u);
-                    } else {
-                        const double2 v = *reinterpret_cast<const double2*>(tl + r * kFBW + sl * VEC);
-                        bits = (v.x == v.x ? 1u : 0u) | (v.y == v.y ? 2u : 0u);
-                    }
-                }
-                bits <<= VEC * (lane % LPW);
-#pragma unroll
-                for (int o = 1; o < LPW; o <<= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);
-                if (lane % LPW == 0) s.mask[r * 4 + sl / LPW] = bits;
-            }
-        }
-        __syncthreads();
-
-        // ---- compact masked cells into the queue (and, when results are not patched into the tile, pass valid cells
-        // through) -- a warp takes whole tile rows: the row's validity is two words of the bitmask, the same for every lane,
-        // so the queue slots come from popcounts instead of ballots, one shared-memory atomic per row.
-        {
-            const int ncols = min(kFW, p.n_out_cols - I0);
-            const uint32_t range_lo = ncols >= 32 ? 0xffffffffu : (1u << ncols) - 1u;
-            const uint32_t range_hi = ncols >= 64 ? 0xffffffffu : (ncols > 32 ? (1u << (ncols - 32)) - 1u : 0u);
-            const uint32_t below = (1u << lane) - 1u;
-            for (int lj = warp; lj < kFH; lj += kWarps) {
-                if (J0 + lj >= p.row_end) break;
-                const uint32_t* const mrow = s.mask + (lj + kFHalo) * 4;
-                const uint32_t v_lo = __funnelshift_r(mrow[0], mrow[1], kFHalo), v_hi = __funnelshift_r(mrow[1], mrow[2], kFHalo);
-                const uint32_t todo_lo = FILL ? ~v_lo & range_lo : range_lo, todo_hi = FILL ? ~v_hi & range_hi : range_hi;
-                const int n_lo = __popc(todo_lo), n_row = n_lo + __popc(todo_hi);
-                int base = 0;
-                if (lane == 0 && n_row) base = atomicAdd(&s.qn, n_row);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (FILL && !kPatch) {
-                    const T* const trow = tl + (lj + kFHalo) * kFBW + kFHalo;
-                    T* const orow = out_tile + lj * p.out_ld;
-                    if ((v_lo & range_lo) >> lane & 1u) __stcs(orow + lane, trow[lane]);
-                    if ((v_hi & range_hi) >> lane & 1u) __stcs(orow + 32 + lane, trow[32 + lane]);
-                }
-                if (todo_lo >> lane & 1u) queue[base + __popc(todo_lo & below)] = static_cast<uint16_t>(lj * kFW + lane);
-                if (todo_hi >> lane & 1u) queue[base + n_lo + __popc(todo_hi & below)] = static_cast<uint16_t>(lj * kFW + 32 + lane);
-            }
-        }
-        __syncthreads();
-
-        // ---- BILINEAR: no search -- the four corners around the query sit in the tile (GridH.cpp:160-210) -----------------
-        if (METHOD == BILINEAR || METHOD == BILINEAR_SEARCH) {
-            const int qn_b = s.qn;
-            for (int q = tid; q < qn_b; q += THREADS) {
-                const int k = queue[q];
-                const int lj = k / kFW, li = k % kFW;
-                const double x = s.x[li], y = s.y[lj];
-                double result = qnan();
-                if (!isnan(x) && !isnan(y)) {
-                    const int x0 = s.cx[li], y0 = s.cy[lj];             // floor(x), floor(y)
-                    const int x1 = min(x0 + 1, p.g.n_lon - 1), y1 = min(y0 + 1, p.g.n_lat - 1);
-                    const double wx = dsub(x, __int2double_rn(x0)), wy = dsub(y, __int2double_rn(y0));
-                    const T* const r0p = tl + (y0 - r0) * kFBW - c0;
-                    const T* const r1p = tl + (y1 - r0) * kFBW - c0;
-                    const double a = static_cast<double>(r0p[x0]), b = static_cast<double>(r0p[x1]);
-                    const double c = static_cast<double>(r1p[x0]), d = static_cast<double>(r1p[x1]);
-                    if (isnan(a) || isnan(b) || isnan(c) || isnan(d)) result = mean_valid4(a, b, c, d);
-                    else {
-                        const double ux = dsub(1.0, wx);
-                        const double lo = dadd(dmul(ux, a), dmul(wx, b));
-                        const double hi = dadd(dmul(ux, c), dmul(wx, d));
-                        result = dadd(dmul(dsub(1.0, wy), lo), dmul(wy, hi));
-                    }
-                }
-                // BILINEAR_SEARCH (opt-in): a query whose four corners are all missing goes on to the ring search
-                if (METHOD == BILINEAR_SEARCH && isnan(result) && !isnan(x) && !isnan(y)) defer[atomicAdd(&s.dn, 1)] = static_cast<uint16_t>(k);
-                else emit(lj, li, static_cast<T>(result));
-            }
-            if (METHOD == BILINEAR_SEARCH) {
-                __syncthreads();
-                const int left = s.dn;
-                for (int q = tid; q < left; q += THREADS) queue[q] = defer[q];
-                __syncthreads();
-                if (tid == 0) { s.qn = left; s.dn = 0; }
-                __syncthreads();
-            }
-        }
-
-        if (METHOD != BILINEAR) {
-            auto window = [&](int row, int wi, int sh) -> uint32_t {       // validity of columns ci-10..ci+10 of a tile row
-                return __funnelshift_r(s.mask[row * 4 + wi], s.mask[row * 4 + wi + 1], sh) & 0x1FFFFFu;
-            };
-            auto to_literal = [&](int k) {                                  // hand a query to the literal per-query path
-                const int slot = atomicAdd(&s.rn, 1);
-                if (slot < kFRedoMax) s.redo[slot] = static_cast<uint16_t>(k);
-                else emit(k / kFW, k % kFW, fill_cell_literal<T, METHOD>(&p, J0 + k / kFW, I0 + k % kFW));
-            };
-
-            // ---- phase A1: the 5 x 5 block around each query's centre decides most searches ---------------------------
-            // (GridH.cpp:48-117: the count is checked after each top/bottom pass and after each left/right pass.)  A query
-            // whose search ends inside the block with at most kFNear candidates takes the near path: its record is the set
-            // of candidate cells.  The others are deferred to the general termination scan (phase A2).
-            const int qn = s.qn;
-            for (int qbase = 0; qbase < qn; qbase += THREADS) {
-                const int q = qbase + tid;
-                const bool live = q < qn;
-                const int k = live ? queue[q] : 0;
-                const int lj = k / kFW, li = k % kFW;
-                uint32_t rec = 0xffffffffu;                                // "no record"
-                int near_bin = -1;
-                if (!live) {
-                } else if (isnan(s.x[li]) || isnan(s.y[lj])) {
-                    emit(lj, li, static_cast<T>(qnan()));                  // query out of bounds
-                } else {
-                    const int ci = s.cx[li] - c0, cj = s.cy[lj] - r0;       // search centre in tile coordinates
-                    if ((ci < 11) | (ci > kFBW - 12) | (cj < 11) | (cj > kFBH - 12)) to_literal(k);   // never for node queries
-                    else {
-                        const int sh0 = ci - 2, wi = sh0 >> 5, sh = sh0 & 31;
-                        uint32_t blk = 0;
-#pragma unroll
-                        for (int dy = -2; dy <= 2; ++dy) {
-                            const uint32_t* mrow = s.mask + (cj + dy) * 4 + wi;
-                            blk |= s.lut[(dy + 2) * 32 + (__funnelshift_r(mrow[0], mrow[1], sh) & 31u)];
-                        }
-                        const int n1 = __popc(blk & kC1), n2 = __popc(blk & kC2), n3 = __popc(blk & kC3), n4 = __popc(blk);
-                        const uint32_t cm = n1 >= 4 ? kC1 : (n2 >= 4 ? kC2 : (n3 >= 4 ? kC3 : kC4));
-                        const int n = n1 >= 4 ? n1 : (n2 >= 4 ? n2 : (n3 >= 4 ? n3 : n4));
-                        if (n >= 4 && n <= kFNear) {
-                            near_bin = kFBinNear + n - 4;
-                            rec = (blk & cm) | (static_cast<uint32_t>(near_bin) << 25);
-                        } else {
-                            defer[atomicAdd(&s.dn, 1)] = static_cast<uint16_t>(q);
-                        }
-                    }
-                }
-                if (near_bin >= 0) atomicAdd(&s.hist[near_bin], 1);
-                if (live) { s.rec[q] = rec; s.reck[q] = static_cast<uint16_t>(k); }
-            }
-            __syncthreads();
-            // ---- phase A2: general termination scan (rings up to radius 10) for the deferred queries ---------------
-            const int dn = s.dn;
-            for (int t = tid; t < dn; t += THREADS) {
-                const int q = defer[t];
-                const int k = s.reck[q];
-                const int lj = k / kFW, li = k % kFW;
-                const int ci = s.cx[li] - c0, cj = s.cy[lj] - r0;
-                const int sh0 = ci - 10, wi = sh0 >> 5, sh = sh0 & 31;
-                uint32_t wt[kFUnroll + 1], wb[kFUnroll + 1];
-                const uint32_t w0 = window(cj, wi, sh);
-                wt[0] = w0; wb[0] = w0;
-                int n = (w0 >> 10) & 1;
-                int r_end = kMaxRadius, lr_end = 1;                         // last ring visited; did its left/right pass run?
-                bool done = false;
-#pragma unroll
-                for (int r = 1; r <= kFUnroll; ++r) {
-                    if (!done) {
-                        wt[r] = window(cj - r, wi, sh); wb[r] = window(cj + r, wi, sh);
-                        const uint32_t tbm = ((2u << (2 * r)) - 1u) << (10 - r);
-                        n += __popc(wt[r] & tbm) + __popc(wb[r] & tbm);
-                        if (n >= 4) { done = true; r_end = r; lr_end = 0; }
-                        else {
-                            const uint32_t lrm = (1u << (10 - r)) | (1u << (10 + r));
-                            int c = __popc(w0 & lrm);
-#pragma unroll
-                            for (int d = 1; d < r; ++d) c += __popc(wt[d] & lrm) + __popc(wb[d] & lrm);
-                            n += c;
-                            if (n >= 4) { done = true; r_end = r; lr_end = 1; }
-                        }
-                    }
-                }
-                for (int r = kFUnroll + 1; r <= kMaxRadius && !done; ++r) {   // sparse neighbourhoods: rolled, windows re-read
-                    const uint32_t tbm = ((2u << (2 * r)) - 1u) << (10 - r);
-                    n += __popc(window(cj - r, wi, sh) & tbm) + __popc(window(cj + r, wi, sh) & tbm);
-                    if (n >= 4) { done = true; r_end = r; lr_end = 0; }
-                    else {
-                        const uint32_t lrm = (1u << (10 - r)) | (1u << (10 + r));
-                        for (int dy = -r + 1; dy <= r - 1; ++dy) n += __popc(window(cj + dy, wi, sh) & lrm);
-                        if (n >= 4) { done = true; r_end = r; lr_end = 1; }
-                    }
-                }
-                if (n > kFNMax) to_literal(k);
+    // ---- BILINEAR: no search -- the four corners around the query sit in the tile (GridH.cpp:160-210) -----------------
+    if (METHOD == BILINEAR || METHOD == BILINEAR_SEARCH) {
+        const int qn_b = s.qn;
+        for (int q = tid; q < qn_b; q += kFThreads) {
+            const int k = queue[q];
+            const int lj = k / kFW, li = k % kFW;
+            const double x = s.x[li], y = s.y[lj];
+            double result = qnan();
+            if (!isnan(x) && !isnan(y)) {
+                const int x0 = s.cx[li], y0 = s.cy[lj];             // floor(x), floor(y)
+                const int x1 = min(x0 + 1, p.g.n_lon - 1), y1 = min(y0 + 1, p.g.n_lat - 1);
+                const double wx = dsub(x, __int2double_rn(x0)), wy = dsub(y, __int2double_rn(y0));
+                const T* const r0p = s.tile + (y0 - r0) * kFBW - c0;
+                const T* const r1p = s.tile + (y1 - r0) * kFBW - c0;
+                const double a = static_cast<double>(r0p[x0]), b = static_cast<double>(r0p[x1]);
+                const double c = static_cast<double>(r1p[x0]), d = static_cast<double>(r1p[x1]);
+                if (isnan(a) || isnan(b) || isnan(c) || isnan(d)) result = mean_valid4(a, b, c, d);
                 else {
-                    const int tcode = r_end <= 3 ? (r_end - 1) * 2 + lr_end : 6;
-                    const int ncls = n < 4 ? 9 : n - 4;                     // n in 4..12 -> 0..8
-                    const int bin = tcode * 10 + ncls;
-                    atomicAdd(&s.hist[bin], 1);
-                    s.rec[q] = static_cast<uint32_t>(r_end) | (static_cast<uint32_t>(lr_end) << 4) |
-                               (static_cast<uint32_t>(n) << 5) | (static_cast<uint32_t>(bin) << 25);
+                    const double ux = dsub(1.0, wx);
+                    const double lo = dadd(dmul(ux, a), dmul(wx, b));
+                    const double hi = dadd(dmul(ux, c), dmul(wx, d));
+                    result = dadd(dmul(dsub(1.0, wy), lo), dmul(wy, hi));
                 }
             }
-            __syncthreads();
-            // ---- order the records by bin: the warps of phase B then run the same code on lists of the same length ----
-            if (warp == 0) {                                               // exclusive scan of the histogram
-                int carry = 0;
-#pragma unroll
-                for (int b0 = 0; b0 < kFBins; b0 += 32) {
-                    const int b = b0 + lane;
-                    const int v = s.hist[b];
-                    int incl = v;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += t;
-                    }
-                    s.hist[b] = carry + incl - v;
-                    if (b == kFBinNear) s.q_near = carry + incl - v;        // first near-path record
-                    carry += __shfl_sync(0xffffffffu, incl, 31);
-                }
-                if (lane == 0) s.qn = carry;                               // records that go to phase B
-            }
-            __syncthreads();
-            {   // scatter: records move from queue order to bin order (read all, sync, then write)
-                uint32_t mine[kPer];
-                uint16_t minek[kPer];
-#pragma unroll
-                for (int i2 = 0; i2 < kPer; ++i2) {
-                    const int q = i2 * THREADS + tid;
-                    mine[i2] = q < qn ? s.rec[q] : 0xffffffffu;
-                    minek[i2] = q < qn ? s.reck[q] : 0;
-                }
-                __syncthreads();
-#pragma unroll
-                for (int i2 = 0; i2 < kPer; ++i2) {
-                    if (mine[i2] != 0xffffffffu) {
-                        const int dst = atomicAdd(&s.hist[mine[i2] >> 25], 1);
-                        s.rec[dst] = mine[i2]; s.reck[dst] = minek[i2];
-                    }
-                }
-            }
-            __syncthreads();
-            const int qb = s.qn, q_near = s.q_near;
+            // BILINEAR_SEARCH (opt-in): a query whose four corners are all missing goes on to the ring search
+            if (METHOD == BILINEAR_SEARCH && isnan(result) && !isnan(x) && !isnan(y)) defer[atomicAdd(&s.dn, 1)] = static_cast<uint16_t>(k);
+            else __stcs(out_tile + lj * p.out_ld + li, static_cast<T>(result));
+        }
+        if (METHOD == BILINEAR) return;
+        __syncthreads();
+        const int left = s.dn;
+        for (int q = tid; q < left; q += kFThreads) queue[q] = defer[q];
+        __syncthreads();
+        if (tid == 0) { s.qn = left; s.dn = 0; }
+        __syncthreads();
+    }
 
-            // ---- phase B, general path (as a function of the record): searches that leave the 5 x 5 block or hold more than
-            // kFNear candidates.  Candidates in list order into a per-thread list in shared memory, the reference's selection
-            // literally on it (squared distances, with the sqrt guard of each comparison), then the method.
-            auto general_query = [&](int q) {
-                const uint32_t rec = s.rec[q];
-                const int k = s.reck[q];
-                const int r_end = rec & 15, lr_end = (rec >> 4) & 1, n = (rec >> 5) & 31;
-                const int lj = k / kFW, li = k % kFW;
-                const int cig = s.cx[li], cjg = s.cy[lj];
-                const int ci = cig - c0, cj = cjg - r0;
-                const int sh0 = ci - 10, wi = sh0 >> 5, sh = sh0 & 31;
-                const double x = s.x[li], y = s.y[lj];
-                const double cxf = dadd(__int2double_rn(cig), 0.5), cyf = dadd(__int2double_rn(cjg), 0.5);
-                const double* const sqx = s.sqx + li * (2 * kFSq + 1) + kFSq;
-                const double* const sqy = s.sqy + lj * (2 * kFSq + 1) + kFSq;
-                auto sqdx = [&](int d) -> double { return (d >= -kFSq && d <= kFSq) ? sqx[d] : sq_offset(cxf, d, x); };
-                auto sqdy = [&](int d) -> double { return (d >= -kFSq && d <= kFSq) ? sqy[d] : sq_offset(cyf, d, y); };
+    auto window = [&](int row, int wi, int sh) -> uint32_t {       // validity of columns ci-10..ci+10 of a tile row
+        return __funnelshift_r(s.mask[row * 4 + wi], s.mask[row * 4 + wi + 1], sh) & 0x1FFFFFu;
+    };
+    auto to_literal = [&](int k) {                                  // hand a query to the literal per-query path
+        const int slot = atomicAdd(&s.rn, 1);
+        if (slot < kFRedoMax) s.redo[slot] = static_cast<uint16_t>(k);
+        else __stcs(out_tile + (k / kFW) * p.out_ld + (k % kFW), fill_cell_literal<T, METHOD>(&p, J0 + k / kFW, I0 + k % kFW));
+    };
 
-                // -- candidates in the reference's enumeration order with their squared distances
-                double* const ld2 = s.d2 + tid;
-                uint16_t* const lcode = s.code + tid;
-                int cnt = 0;
-                auto push = [&](int dx, int dy, double d2) {
-                    ld2[cnt * THREADS] = d2;
-                    lcode[cnt * THREADS] = static_cast<uint16_t>((dy + 10) * 32 + (dx + 10));
-                    ++cnt;
-                };
-                uint32_t wt[kFUnroll + 1], wb[kFUnroll + 1];
-                const uint32_t w0 = window(cj, wi, sh);
-                wt[0] = w0; wb[0] = w0;
-                if ((w0 >> 10) & 1) push(0, 0, dadd(sqdx(0), sqdy(0)));
+    // ---- phase A1: the 5 x 5 block around each query's centre decides most searches ---------------------------
+    // (GridH.cpp:48-117: the count is checked after each top/bottom pass and after each left/right pass.)  A query
+    // whose search ends inside the block with at most kFNear candidates takes the near path: its record is the set
+    // of candidate cells.  The others are deferred to the general termination scan (phase A2).
+    const int qn = s.qn;
+    for (int qbase = 0; qbase < qn; qbase += kFThreads) {
+        const int q = qbase + tid;
+        const bool live = q < qn;
+        const int k = live ? queue[q] : 0;
+        const int lj = k / kFW, li = k % kFW;
+        uint32_t rec = 0xffffffffu;                                // "no record"
+        int near_bin = -1;
+        if (!live) {
+        } else if (isnan(s.x[li]) || isnan(s.y[lj])) {
+            __stcs(out_tile + lj * p.out_ld + li, static_cast<T>(qnan()));   // query out of bounds
+        } else {
+            const int ci = s.cx[li] - c0, cj = s.cy[lj] - r0;       // search centre in tile coordinates
+            if ((ci < 11) | (ci > kFBW - 12) | (cj < 11) | (cj > kFBH - 12)) to_literal(k);   // never for node queries
+            else {
+                const int sh0 = ci - 2, wi = sh0 >> 5, sh = sh0 & 31;
+                uint32_t blk = 0;
 #pragma unroll
-                for (int r = 1; r <= kFUnroll; ++r) {
-                    if (r <= r_end) {
-                        wt[r] = window(cj - r, wi, sh); wb[r] = window(cj + r, wi, sh);
-                        const uint32_t tbm = ((2u << (2 * r)) - 1u) << (10 - r);
-                        const uint32_t top = wt[r] & tbm, bot = wb[r] & tbm;
-                        uint32_t m = top | bot;
-                        if (m) {
-                            const double dyt = sqdy(-r), dyb = sqdy(r);
-                            while (m) {                                   // columns left to right; top before bottom
-                                const int b = __ffs(m) - 1;
-                                m &= m - 1;
-                                const double dx2 = sqdx(b - 10);
-                                if ((top >> b) & 1u) push(b - 10, -r, dadd(dx2, dyt));
-                                if ((bot >> b) & 1u) push(b - 10, r, dadd(dx2, dyb));
-                            }
-                        }
-                        if (r < r_end || lr_end) {
-                            const uint32_t lb = 1u << (10 - r), rb = 1u << (10 + r);
-                            uint32_t any = (w0 & (lb | rb));
+                for (int dy = -2; dy <= 2; ++dy) {
+                    const uint32_t* mrow = s.mask + (cj + dy) * 4 + wi;
+                    blk |= s.lut[(dy + 2) * 32 + (__funnelshift_r(mrow[0], mrow[1], sh) & 31u)];
+                }
+                const int n1 = __popc(blk & kC1), n2 = __popc(blk & kC2), n3 = __popc(blk & kC3), n4 = __popc(blk);
+                const uint32_t cm = n1 >= 4 ? kC1 : (n2 >= 4 ? kC2 : (n3 >= 4 ? kC3 : kC4));
+                const int n = n1 >= 4 ? n1 : (n2 >= 4 ? n2 : (n3 >= 4 ? n3 : n4));
+                if (n >= 4 && n <= kFNear) {
+                    near_bin = kFBinNear + n - 4;
+                    rec = (blk & cm) | (static_cast<uint32_t>(near_bin) << 25);
+                } else {
+                    defer[atomicAdd(&s.dn, 1)] = static_cast<uint16_t>(q);
+                }
+            }
+        }
+        if (near_bin >= 0) atomicAdd(&s.hist[near_bin], 1);
+        if (live) { s.rec[q] = rec; s.reck[q] = static_cast<uint16_t>(k); }
+    }
+    __syncthreads();
+    // ---- phase A2: general termination scan (rings up to radius 10) for the deferred queries ---------------
+    const int dn = s.dn;
+    for (int t = tid; t < dn; t += kFThreads) {
+        const int q = defer[t];
+        const int k = s.reck[q];
+        const int lj = k / kFW, li = k % kFW;
+        const int ci = s.cx[li] - c0, cj = s.cy[lj] - r0;
+        const int sh0 = ci - 10, wi = sh0 >> 5, sh = sh0 & 31;
+        uint32_t wt[kFUnroll + 1], wb[kFUnroll + 1];
+        const uint32_t w0 = window(cj, wi, sh);
+        wt[0] = w0; wb[0] = w0;
+        int n = (w0 >> 10) & 1;
+        int r_end = kMaxRadius, lr_end = 1;                         // last ring visited; did its left/right pass run?
+        bool done = false;
 #pragma unroll
-                            for (int d = 1; d < r; ++d) any |= (wt[d] | wb[d]) & (lb | rb);
-                            if (any) {
-                                const double dxl = sqdx(-r), dxr = sqdx(r);
+        for (int r = 1; r <= kFUnroll; ++r) {
+            if (!done) {
+                wt[r] = window(cj - r, wi, sh); wb[r] = window(cj + r, wi, sh);
+                const uint32_t tbm = ((2u << (2 * r)) - 1u) << (10 - r);
+                n += __popc(wt[r] & tbm) + __popc(wb[r] & tbm);
+                if (n >= 4) { done = true; r_end = r; lr_end = 0; }
+                else {
+                    const uint32_t lrm = (1u << (10 - r)) | (1u << (10 + r));
+                    int c = __popc(w0 & lrm);
 #pragma unroll
-                                for (int dy = -r + 1; dy <= r - 1; ++dy) {   // rows top to bottom; left before right
-                                    const uint32_t wr = dy < 0 ? wt[-dy] : (dy == 0 ? w0 : wb[dy]);
-                                    if (wr & (lb | rb)) {
-                                        const double dy2 = sqdy(dy);
-                                        if (wr & lb) push(-r, dy, dadd(dxl, dy2));
-                                        if (wr & rb) push(r, dy, dadd(dxr, dy2));
-                                    }
-                                }
-                            }
-                        }
+                    for (int d = 1; d < r; ++d) c += __popc(wt[d] & lrm) + __popc(wb[d] & lrm);
+                    n += c;
+                    if (n >= 4) { done = true; r_end = r; lr_end = 1; }
+                }
+            }
+        }
+        for (int r = kFUnroll + 1; r <= kMaxRadius && !done; ++r) {   // sparse neighbourhoods: rolled, windows re-read
+            const uint32_t tbm = ((2u << (2 * r)) - 1u) << (10 - r);
+            n += __popc(window(cj - r, wi, sh) & tbm) + __popc(window(cj + r, wi, sh) & tbm);
+            if (n >= 4) { done = true; r_end = r; lr_end = 0; }
+            else {
+                const uint32_t lrm = (1u << (10 - r)) | (1u << (10 + r));
+                for (int dy = -r + 1; dy <= r - 1; ++dy) n += __popc(window(cj + dy, wi, sh) & lrm);
+                if (n >= 4) { done = true; r_end = r; lr_end = 1; }
+            }
+        }
+        if (n > kFNMax) to_literal(k);
+        else {
+            const int tcode = r_end <= 3 ? (r_end - 1) * 2 + lr_end : 6;
+            const int ncls = n < 4 ? 9 : n - 4;                     // n in 4..12 -> 0..8
+            const int bin = tcode * 10 + ncls;
+            atomicAdd(&s.hist[bin], 1);
+            s.rec[q] = static_cast<uint32_t>(r_end) | (static_cast<uint32_t>(lr_end) << 4) |
+                       (static_cast<uint32_t>(n) << 5) | (static_cast<uint32_t>(bin) << 25);
+        }
+    }
+    __syncthreads();
+    // ---- order the records by bin: the warps of phase B then run the same code on lists of the same length ----
+    if (warp == 0) {                                               // exclusive scan of the histogram
+        int carry = 0;
+#pragma unroll
+        for (int b0 = 0; b0 < kFBins; b0 += 32) {
+            const int b = b0 + lane;
+            const int v = s.hist[b];
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            s.hist[b] = carry + incl - v;
+            if (b == kFBinNear) s.q_near = carry + incl - v;        // first near-path record
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) s.qn = carry;                               // records that go to phase B
+    }
+    __syncthreads();
+    {   // scatter: records move from queue order to bin order (read all, sync, then write)
+        uint32_t mine[kFPer];
+        uint16_t minek[kFPer];
+#pragma unroll
+        for (int it = 0; it < kFPer; ++it) {
+            const int q = it * kFThreads + tid;
+            mine[it] = q < qn ? s.rec[q] : 0xffffffffu;
+            minek[it] = q < qn ? s.reck[q] : 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < kFPer; ++it) {
+            if (mine[it] != 0xffffffffu) {
+                const int dst = atomicAdd(&s.hist[mine[it] >> 25], 1);
+                s.rec[dst] = mine[it]; s.reck[dst] = minek[it];
+            }
+        }
+    }
+    __syncthreads();
+    const int qb = s.qn, q_near = s.q_near;
+
+    // ---- phase B, general path (as a function of the record): searches that leave the 5 x 5 block or hold more than
+    // kFNear candidates.  Candidates in list order into a per-thread list in shared memory, the reference's selection
+    // literally on it (squared distances, with the sqrt guard of each comparison), then the method.
+    auto general_query = [&](int q) {
+        const uint32_t rec = s.rec[q];
+        const int k = s.reck[q];
+        const int r_end = rec & 15, lr_end = (rec >> 4) & 1, n = (rec >> 5) & 31;
+        const int lj = k / kFW, li = k % kFW;
+        const int cig = s.cx[li], cjg = s.cy[lj];
+        const int ci = cig - c0, cj = cjg - r0;
+        const int sh0 = ci - 10, wi = sh0 >> 5, sh = sh0 & 31;
+        const double x = s.x[li], y = s.y[lj];
+        const double cxf = dadd(__int2double_rn(cig), 0.5), cyf = dadd(__int2double_rn(cjg), 0.5);
+        const double* const sqx = s.sqx + li * (2 * kFSq + 1) + kFSq;
+        const double* const sqy = s.sqy + lj * (2 * kFSq + 1) + kFSq;
+        auto sqdx = [&](int d) -> double { return (d >= -kFSq && d <= kFSq) ? sqx[d] : sq_offset(cxf, d, x); };
+        auto sqdy = [&](int d) -> double { return (d >= -kFSq && d <= kFSq) ? sqy[d] : sq_offset(cyf, d, y); };
+
+        // -- candidates in the reference's enumeration order with their squared distances
+        double* const ld2 = s.d2 + tid;
+        uint16_t* const lcode = s.code + tid;
+        int cnt = 0;
+        auto push = [&](int dx, int dy, double d2) {
+            ld2[cnt * kFThreads] = d2;
+            lcode[cnt * kFThreads] = static_cast<uint16_t>((dy + 10) * 32 + (dx + 10));
+            ++cnt;
+        };
+        uint32_t wt[kFUnroll + 1], wb[kFUnroll + 1];
+        const uint32_t w0 = window(cj, wi, sh);
+        wt[0] = w0; wb[0] = w0;
+        if ((w0 >> 10) & 1) push(0, 0, dadd(sqdx(0), sqdy(0)));
+#pragma unroll
+        for (int r = 1; r <= kFUnroll; ++r) {
+            if (r <= r_end) {
+                wt[r] = window(cj - r, wi, sh); wb[r] = window(cj + r, wi, sh);
+                const uint32_t tbm = ((2u << (2 * r)) - 1u) << (10 - r);
+                const uint32_t top = wt[r] & tbm, bot = wb[r] & tbm;
+                uint32_t m = top | bot;
+                if (m) {
+                    const double dyt = sqdy(-r), dyb = sqdy(r);
+                    while (m) {                                   // columns left to right; top before bottom
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        const double dx2 = sqdx(b - 10);
+                        if ((top >> b) & 1u) push(b - 10, -r, dadd(dx2, dyt));
+                        if ((bot >> b) & 1u) push(b - 10, r, dadd(dx2, dyb));
                     }
                 }
-                for (int r = kFUnroll + 1; r <= r_end; ++r) {               // sparse neighbourhoods: the same walk, rolled
-                    const uint32_t tbm = ((2u << (2 * r)) - 1u) << (10 - r);
-                    const uint32_t top = window(cj - r, wi, sh) & tbm, bot = window(cj + r, wi, sh) & tbm;
-                    uint32_t m = top | bot;
-                    if (m) {
-                        const double dyt = sqdy(-r), dyb = sqdy(r);
-                        while (m) {
-                            const int b = __ffs(m) - 1;
-                            m &= m - 1;
-                            const double dx2 = sqdx(b - 10);
-                            if ((top >> b) & 1u) push(b - 10, -r, dadd(dx2, dyt));
-                            if ((bot >> b) & 1u) push(b - 10, r, dadd(dx2, dyb));
-                        }
-                    }
-                    if (r < r_end || lr_end) {
-                        const uint32_t lb = 1u << (10 - r), rb = 1u << (10 + r);
-                        double dxl = 0.0, dxr = 0.0;
-                        bool have = false;
-                        for (int dy = -r + 1; dy <= r - 1; ++dy) {
-                            const uint32_t wr = window(cj + dy, wi, sh);
+                if (r < r_end || lr_end) {
+                    const uint32_t lb = 1u << (10 - r), rb = 1u << (10 + r);
+                    uint32_t any = (w0 & (lb | rb));
+#pragma unroll
+                    for (int d = 1; d < r; ++d) any |= (wt[d] | wb[d]) & (lb | rb);
+                    if (any) {
+                        const double dxl = sqdx(-r), dxr = sqdx(r);
+#pragma unroll
+                        for (int dy = -r + 1; dy <= r - 1; ++dy) {   // rows top to bottom; left before right
+                            const uint32_t wr = dy < 0 ? wt[-dy] : (dy == 0 ? w0 : wb[dy]);
                             if (wr & (lb | rb)) {
-                                if (!have) { dxl = sqdx(-r); dxr = sqdx(r); have = true; }
                                 const double dy2 = sqdy(dy);
                                 if (wr & lb) push(-r, dy, dadd(dxl, dy2));
                                 if (wr & rb) push(r, dy, dadd(dxr, dy2));
@@ -765,158 +667,156 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                         }
                     }
                 }
-                // cnt == n by construction (phase A counted the same bits)
-                // -- the reference's partial selection sort with swaps (GridH.cpp:123-140) on squared distances.
-                // NN only needs the first pick: pass 0 (with fewer than four candidates the oracle's "first strict
-                // minimum" is the same scan); the other methods run the four passes when four candidates exist.
-                bool unsure = (cnt != n);
-                const int n_pass = METHOD == NN ? (cnt > 0 ? 1 : 0) : (cnt >= 4 ? 4 : 0);
-                for (int m = 0; m < n_pass; ++m) {
-                    int best = m;
-                    const double dm = ld2[m * THREADS];
-                    double dbest = dm, thr = dmul(dm, kSafeRatio);
-                    for (int kk = m + 1; kk < cnt; ++kk) {
-                        const double dk = ld2[kk * THREADS];
-                        if (dk < thr) { best = kk; dbest = dk; thr = dmul(dk, kSafeRatio); }
-                        else if (dk < dbest) unsure = true;                // within a few ulps: sqrt may tie
-                    }
-                    if (best != m) {
-                        ld2[m * THREADS] = dbest; ld2[best * THREADS] = dm;
-                        const uint16_t cm = lcode[m * THREADS];
-                        lcode[m * THREADS] = lcode[best * THREADS]; lcode[best * THREADS] = cm;
-                    }
-                }
-                if (unsure) { to_literal(k); return; }
-                if (cnt >= 4) {
-                    T v[4];
-                    double d2v[4];
-                    int pi[4], pj[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int code = lcode[e * THREADS];
-                        const int dx = (code & 31) - 10, dy = (code >> 5) - 10;
-                        v[e] = tl[(cj + dy) * kFBW + ci + dx];
-                        d2v[e] = ld2[e * THREADS];
-                        pi[e] = cig + dx; pj[e] = cjg + dy;
-                    }
-                    emit(lj, li, finish_four<T, METHOD>(p, v, d2v, pi, pj, I0 + li, J0 + lj));
-                } else {                                                    // the search ran out of rings (GridH.cpp:291-298)
-                    double fv[3], fd[3];
-#pragma unroll
-                    for (int e = 0; e < 3; ++e) {
-                        const int code = e < cnt ? lcode[e * THREADS] : (10 * 32 + 10);
-                        fv[e] = static_cast<double>(tl[(cj + (code >> 5) - 10) * kFBW + ci + (code & 31) - 10]);
-                        fd[e] = e < cnt ? ld2[e * THREADS] : 0.0;
-                    }
-                    emit(lj, li, finish_few<T, METHOD>(cnt, fv[0], fv[1], fv[2], fd[0], fd[1], fd[2]));
-                }
-            };
-
-            // ---- phase B: warps draw chunks of 32 records from a CTA-wide counter ------------------------------------------------
-            // General-path chunks first (they are the long ones), then the near-path chunks; the bins are ordered by candidate
-            // count, so a near chunk's queries have (nearly) the same count and the list length is a compile-time constant
-            // chosen per chunk.  Drawing chunks keeps every warp busy until the records run out whatever the mix.
-            {
-                const int gen_chunks = (q_near + 31) >> 5, all_chunks = gen_chunks + ((qb - q_near + 31) >> 5);
-                for (;;) {
-                    int ch = 0;
-                    if (lane == 0) ch = atomicAdd(&s.next, 1);
-                    ch = __shfl_sync(0xffffffffu, ch, 0);
-                    if (ch >= all_chunks) break;
-                    if (ch < gen_chunks) {
-                        const int q = ch * 32 + lane;
-                        if (q < q_near) general_query(q);
-                        __syncwarp();
-                        continue;
-                    }
-                    const int q = q_near + (ch - gen_chunks) * 32 + lane;
-                    const bool active = q < qb;
-                    const uint32_t cand = active ? (s.rec[q] & kC4) : 0u;
-                    const int nmax = __reduce_max_sync(0xffffffffu, __popc(cand));
-                    if (active) {
-                        const int k = s.reck[q];
-                        bool ok;
-                        if (nmax <= 4) ok = near_query<T, METHOD, 4, false>(s, p, tl, emit, cand, q, k, c0, r0, I0, J0);
-                        else if (nmax <= 6) ok = near_query<T, METHOD, 6, false>(s, p, tl, emit, cand, q, k, c0, r0, I0, J0);
-                        else ok = near_query<T, METHOD, kFNear, false>(s, p, tl, emit, cand, q, k, c0, r0, I0, J0);
-                        if (!ok) {
-                            const int slot = atomicAdd(&s.tn, 1);
-                            if (slot < kFReplayMax) s.replay[slot] = static_cast<uint16_t>(q);
-                            else to_literal(k);
-                        }
-                    }
-                    __syncwarp();
+            }
+        }
+        for (int r = kFUnroll + 1; r <= r_end; ++r) {               // sparse neighbourhoods: the same walk, rolled
+            const uint32_t tbm = ((2u << (2 * r)) - 1u) << (10 - r);
+            const uint32_t top = window(cj - r, wi, sh) & tbm, bot = window(cj + r, wi, sh) & tbm;
+            uint32_t m = top | bot;
+            if (m) {
+                const double dyt = sqdy(-r), dyb = sqdy(r);
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    const double dx2 = sqdx(b - 10);
+                    if ((top >> b) & 1u) push(b - 10, -r, dadd(dx2, dyt));
+                    if ((bot >> b) & 1u) push(b - 10, r, dadd(dx2, dyb));
                 }
             }
-            __syncthreads();
-            // ---- replay of the near-path queries that met a near tie: the same selection on square-rooted distances ----------
-            const int tn = min(s.tn, kFReplayMax);
-            for (int t = tid; t < tn; t += THREADS) {
-                const int q = s.replay[t];
-                near_query<T, METHOD, kFNear, true>(s, p, tl, emit, s.rec[q] & kC4, q, s.reck[q], c0, r0, I0, J0);
-            }
-            __syncthreads();
-            // ---- kriging of the near-path picks: full warps, nothing else live ------------------------------------------------
-            if (METHOD == KRIGING) {
-                for (int q = q_near + tid; q < qb; q += THREADS) {
-                    const uint32_t rec = s.rec[q];
-                    if ((rec >> 25) != 127u) continue;                      // went to the literal path
-                    const int k = s.reck[q];
-                    const int lj = k / kFW, li = k % kFW;
-                    const int cig = s.cx[li], cjg = s.cy[lj];
-                    const T* const centre = tl + (cjg - r0) * kFBW + (cig - c0);
-                    Picked pk;
-                    pk.found = 4;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int c = (rec >> (5 * e)) & 31;
-                        const int dxy = s.cell_dxy[c];
-                        pk.i[e] = cig + static_cast<int16_t>(dxy & 0xffff); pk.j[e] = cjg + (dxy >> 16);
-                        pk.v[e] = static_cast<double>(centre[s.cell_tile[c]]);
-                        pk.d[e] = 0.0;
+            if (r < r_end || lr_end) {
+                const uint32_t lb = 1u << (10 - r), rb = 1u << (10 + r);
+                double dxl = 0.0, dxr = 0.0;
+                bool have = false;
+                for (int dy = -r + 1; dy <= r - 1; ++dy) {
+                    const uint32_t wr = window(cj + dy, wi, sh);
+                    if (wr & (lb | rb)) {
+                        if (!have) { dxl = sqdx(-r); dxr = sqdx(r); have = true; }
+                        const double dy2 = sqdy(dy);
+                        if (wr & lb) push(-r, dy, dadd(dxl, dy2));
+                        if (wr & rb) push(r, dy, dadd(dxr, dy2));
                     }
-                    emit(lj, li, static_cast<T>(kriging_from_picked(p.g, pk, __ldg(p.lon.coord + I0 + li), __ldg(p.lat.coord + J0 + lj))));
-                }
-            }
-            // ---- queries the bitmask paths handed back: literal per-query evaluation ---------------------------------
-            const int rn = min(s.rn, kFRedoMax);
-            for (int q = tid; q < rn; q += THREADS) {
-                const int k = s.redo[q];
-                emit(k / kFW, k % kFW, fill_cell_literal<T, METHOD>(&p, J0 + k / kFW, I0 + k % kFW));
-            }
-        }  // METHOD != BILINEAR
-
-        // ---- the finished tile leaves: pass-through cells and patched results in one coalesced sweep ----------------------
-        if (kPatch) {
-            __syncthreads();
-            constexpr int VEC = 16 / static_cast<int>(sizeof(T)), VPR = kFW / VEC;
-            const int nrows = static_cast<int>(min(static_cast<int64_t>(kFH), p.row_end - J0));
-            const int ncols = min(kFW, p.n_out_cols - I0);
-            const T* const core = tl + kFHalo * kFBW + kFHalo;
-            if (p.vec_ok) {
-                for (int k = tid; k < nrows * VPR; k += THREADS) {
-                    const int lj = k / VPR, col = (k - lj * VPR) * VEC;
-                    const T* const src = core + lj * kFBW + col;
-                    T* const dst = out_tile + lj * p.out_ld + col;
-                    if (col + VEC <= ncols) {
-                        if constexpr (sizeof(T) == 4) __stcs(reinterpret_cast<float4*>(dst), *reinterpret_cast<const float4*>(src));
-                        else __stcs(reinterpret_cast<double2*>(dst), *reinterpret_cast<const double2*>(src));
-                    } else {
-                        for (int c = 0; col + c < ncols; ++c) __stcs(dst + c, src[c]);
-                    }
-                }
-            } else {
-                for (int k = tid; k < nrows * kFW; k += THREADS) {
-                    const int lj = k / kFW, li = k - lj * kFW;
-                    if (li < ncols) __stcs(out_tile + lj * p.out_ld + li, core[lj * kFBW + li]);
                 }
             }
         }
-        // every generic access to this buffer (and to the per-tile tables) is done before the next iteration's TMA
-        // request may overwrite it
-        if (p.use_tma) fence_proxy_async_smem();
-        __syncthreads();
-        if (STAGES == 1 && p.use_tma && tid == 0 && tile + static_cast<int>(gridDim.x) < p.n_tiles) request_tile(tile + gridDim.x, 0);
+        // cnt == n by construction (phase A counted the same bits)
+        // -- the reference's partial selection sort with swaps (GridH.cpp:123-140) on squared distances.
+        // NN only needs the first pick: pass 0 (with fewer than four candidates the oracle's "first strict
+        // minimum" is the same scan); the other methods run the four passes when four candidates exist.
+        bool unsure = (cnt != n);
+        const int n_pass = METHOD == NN ? (cnt > 0 ? 1 : 0) : (cnt >= 4 ? 4 : 0);
+        for (int m = 0; m < n_pass; ++m) {
+            int best = m;
+            const double dm = ld2[m * kFThreads];
+            double dbest = dm, thr = dmul(dm, kSafeRatio);
+            for (int kk = m + 1; kk < cnt; ++kk) {
+                const double dk = ld2[kk * kFThreads];
+                if (dk < thr) { best = kk; dbest = dk; thr = dmul(dk, kSafeRatio); }
+                else if (dk < dbest) unsure = true;                // within a few ulps: sqrt may tie
+            }
+            if (best != m) {
+                ld2[m * kFThreads] = dbest; ld2[best * kFThreads] = dm;
+                const uint16_t cm = lcode[m * kFThreads];
+                lcode[m * kFThreads] = lcode[best * kFThreads]; lcode[best * kFThreads] = cm;
+            }
+        }
+        if (unsure) { to_literal(k); return; }
+        if (cnt >= 4) {
+            T v[4];
+            double d2v[4];
+            int pi[4], pj[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int code = lcode[e * kFThreads];
+                const int dx = (code & 31) - 10, dy = (code >> 5) - 10;
+                v[e] = s.tile[(cj + dy) * kFBW + ci + dx];
+                d2v[e] = ld2[e * kFThreads];
+                pi[e] = cig + dx; pj[e] = cjg + dy;
+            }
+            __stcs(out_tile + lj * p.out_ld + li, finish_four<T, METHOD>(p, v, d2v, pi, pj, I0 + li, J0 + lj));
+        } else {                                                    // the search ran out of rings (GridH.cpp:291-298)
+            double fv[3], fd[3];
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                const int code = e < cnt ? lcode[e * kFThreads] : (10 * 32 + 10);
+                fv[e] = static_cast<double>(s.tile[(cj + (code >> 5) - 10) * kFBW + ci + (code & 31) - 10]);
+                fd[e] = e < cnt ? ld2[e * kFThreads] : 0.0;
+            }
+            __stcs(out_tile + lj * p.out_ld + li, finish_few<T, METHOD>(cnt, fv[0], fv[1], fv[2], fd[0], fd[1], fd[2]));
+        }
+    };
+
+    // ---- phase B: warps draw chunks of 32 records from a CTA-wide counter ------------------------------------------------
+    // General-path chunks first (they are the long ones), then the near-path chunks; the bins are ordered by candidate
+    // count, so a near chunk's queries have (nearly) the same count and the list length is a compile-time constant
+    // chosen per chunk.  Drawing chunks keeps every warp busy until the records run out whatever the mix.
+    {
+        const int gen_chunks = (q_near + 31) >> 5, all_chunks = gen_chunks + ((qb - q_near + 31) >> 5);
+        for (;;) {
+            int ch = 0;
+            if (lane == 0) ch = atomicAdd(&s.next, 1);
+            ch = __shfl_sync(0xffffffffu, ch, 0);
+            if (ch >= all_chunks) break;
+            if (ch < gen_chunks) {
+                const int q = ch * 32 + lane;
+                if (q < q_near) general_query(q);
+                __syncwarp();
+                continue;
+            }
+            const int q = q_near + (ch - gen_chunks) * 32 + lane;
+            const bool active = q < qb;
+            const uint32_t cand = active ? (s.rec[q] & kC4) : 0u;
+            const int nmax = __reduce_max_sync(0xffffffffu, __popc(cand));
+            if (active) {
+                const int k = s.reck[q];
+                bool ok;
+                if (nmax <= 4) ok = near_query<T, METHOD, 4, false>(s, p, cand, q, k, c0, r0, I0, J0, out_tile);
+                else if (nmax <= 6) ok = near_query<T, METHOD, 6, false>(s, p, cand, q, k, c0, r0, I0, J0, out_tile);
+                else ok = near_query<T, METHOD, kFNear, false>(s, p, cand, q, k, c0, r0, I0, J0, out_tile);
+                if (!ok) {
+                    const int slot = atomicAdd(&s.tn, 1);
+                    if (slot < kFReplayMax) s.replay[slot] = static_cast<uint16_t>(q);
+                    else to_literal(k);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // ---- replay of the near-path queries that met a near tie: the same selection on square-rooted distances ----------
+    const int tn = min(s.tn, kFReplayMax);
+    for (int t = tid; t < tn; t += kFThreads) {
+        const int q = s.replay[t];
+        near_query<T, METHOD, kFNear, true>(s, p, s.rec[q] & kC4, q, s.reck[q], c0, r0, I0, J0, out_tile);
+    }
+    __syncthreads();
+    // ---- kriging of the near-path picks: full warps, nothing else live ------------------------------------------------
+    if (METHOD == KRIGING) {
+        for (int q = q_near + tid; q < qb; q += kFThreads) {
+            const uint32_t rec = s.rec[q];
+            if ((rec >> 25) != 127u) continue;                      // went to the literal path
+            const int k = s.reck[q];
+            const int lj = k / kFW, li = k % kFW;
+            const int cig = s.cx[li], cjg = s.cy[lj];
+            const T* const centre = s.tile + (cjg - r0) * kFBW + (cig - c0);
+            Picked pk;
+            pk.found = 4;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = (rec >> (5 * e)) & 31;
+                const int dxy = s.cell_dxy[c];
+                pk.i[e] = cig + static_cast<int16_t>(dxy & 0xffff); pk.j[e] = cjg + (dxy >> 16);
+                pk.v[e] = static_cast<double>(centre[s.cell_tile[c]]);
+                pk.d[e] = 0.0;
+            }
+            __stcs(out_tile + lj * p.out_ld + li,
+                   static_cast<T>(kriging_from_picked(p.g, pk, __ldg(p.lon.coord + I0 + li), __ldg(p.lat.coord + J0 + lj))));
+        }
+    }
+    // ---- queries the bitmask paths handed back: literal per-query evaluation ---------------------------------
+    const int rn = min(s.rn, kFRedoMax);
+    for (int q = tid; q < rn; q += kFThreads) {
+        const int k = s.redo[q];
+        __stcs(out_tile + (k / kFW) * p.out_ld + (k % kFW), fill_cell_literal<T, METHOD>(&p, J0 + k / kFW, I0 + k % kFW));
     }
 }
 
@@ -1071,27 +971,6 @@ static cudaError_t fill_params(const GridDesc& d, const AxisTables& lat, const A
     return cudaSuccess;
 }
 
-template <typename T, int METHOD, bool FILL, int THREADS, int STAGES, bool PATCH = true>
-static cudaError_t launch_fill_cfg(const GridDesc& d, const AxisTables& lat, const AxisTables& lon, int64_t row_begin,
-                                   int64_t row_end, void* out, int64_t out_ld, cudaStream_t st, LaunchInfo* info) {
-    FillParams<T> p;
-    cudaError_t e = fill_params<T>(d, lat, lon, row_begin, row_end, out, out_ld, FILL, kFW, kFH, &p);
-    if (e != cudaSuccess) return e;
-    CUtensorMap tmap;
-    memset(&tmap, 0, sizeof tmap);
-    p.use_tma = make_grid_tensor_map(d, kFBW, kFBH, &tmap, /*nan_fill=*/true) ? 1 : 0;
-    auto kern = fill_tiled_kernel<T, METHOD, FILL, THREADS, STAGES, PATCH>;
-    const size_t smem = sizeof(FillSmem<T, THREADS, STAGES>);
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-    static const int slots = resident_ctas(kern, THREADS, smem);  // per instantiation; every device of a box is alike
-    static const bool one_tile_per_cta = getenv("AUVI_FILL_ONE_TILE") != nullptr;   // A/B: the non-persistent launch shape
-    const int grid = (p.n_tiles < slots || one_tile_per_cta) ? p.n_tiles : slots;
-    kern<<<grid, THREADS, smem, st>>>(tmap, p);
-    if (info) { info->launches += 1; info->used_tma = p.use_tma; }
-    return cudaGetLastError();
-}
-
 template <typename T>
 static cudaError_t launch_bilinear_fill(const GridDesc& d, const AxisTables& lat, const AxisTables& lon, int64_t row_begin,
                                         int64_t row_end, void* out, int64_t out_ld, cudaStream_t st, LaunchInfo* info) {
@@ -1112,9 +991,6 @@ static cudaError_t launch_bilinear_fill(const GridDesc& d, const AxisTables& lat
     return cudaGetLastError();
 }
 
-// Shape of the persistent CTAs.  FP32 grids: 384 threads, two-deep TMA ring, two CTAs per SM (24 warps); FP64 grids: the
-// ring does not fit twice, 384 threads with one buffer + L2 prefetch.  AUVI_FILL_CFG=1 selects the round-1 shape (256
-// threads, one buffer, three CTAs per SM) for A/B measurements.
 template <typename T, int METHOD, bool FILL>
 static cudaError_t launch_fill_t(const GridDesc& d, const AxisTables& lat, const AxisTables& lon, int64_t row_begin,
                                  int64_t row_end, void* out, int64_t out_ld, cudaStream_t st, LaunchInfo* info) {
@@ -1127,13 +1003,29 @@ static cudaError_t launch_fill_t(const GridDesc& d, const AxisTables& lat, const
     if constexpr (METHOD == BILINEAR && FILL) {
         return launch_bilinear_fill<T>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
     } else {
-        static const int cfg = [] { const char* e = getenv("AUVI_FILL_CFG"); return e ? atoi(e) : 0; }();
-        if (cfg == 1) return launch_fill_cfg<T, METHOD, FILL, 256, 1>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
-        if constexpr (METHOD == IDW && FILL && sizeof(T) == 4) {   // A/B only: results stored per query instead of patched
-            if (cfg == 2) return launch_fill_cfg<T, METHOD, FILL, 256, 1, false>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
-            if (cfg == 3) return launch_fill_cfg<T, METHOD, FILL, 384, 2, false>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
-        }
-        return launch_fill_cfg<T, METHOD, FILL, 384, sizeof(T) == 4 ? 2 : 1>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
+        FillParams<T> p;
+        p.g = make_view<T>(d);
+        p.lat = FillAxis{lat.coord, lat.pos, lat.base};
+        p.lon = FillAxis{lon.coord, lon.pos, lon.base};
+        p.row_begin = row_begin; p.row_end = row_end;
+        p.rows_resident_lo = d.row0; p.rows_resident_hi = d.row0 + d.rows;
+        p.out = static_cast<T*>(out); p.out_ld = out_ld;
+        p.n_out_cols = lon.n;
+        p.f_lat = d.n_lat > 1 ? (lat.n - 1) / (d.n_lat - 1) : 1;
+        p.f_lon = d.n_lon > 1 ? (lon.n - 1) / (d.n_lon - 1) : 1;
+        p.tiles_x = 0; p.n_tiles = 0; p.vec_ok = 0;
+        if (p.f_lat < 1 || p.f_lon < 1 || (FILL && (p.f_lat != 1 || p.f_lon != 1))) return cudaErrorInvalidValue;
+        CUtensorMap tmap;
+        memset(&tmap, 0, sizeof tmap);
+        p.use_tma = make_grid_tensor_map(d, kFBW, kFBH, &tmap, /*nan_fill=*/true) ? 1 : 0;
+        auto kern = fill_tiled_kernel<T, METHOD, FILL>;
+        const size_t smem = sizeof(FillSmem<T>);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        dim3 grid(static_cast<unsigned>((lon.n + kFW - 1) / kFW), static_cast<unsigned>((row_end - row_begin + kFH - 1) / kFH));
+        kern<<<grid, kFThreads, smem, st>>>(tmap, p);
+        if (info) { info->launches += 1; info->used_tma = p.use_tma; }
+        return cudaGetLastError();
     }
 }
 

@@ -243,3 +243,52 @@ def lattice_queries(n_lat, n_lon, min_lon, max_lon, min_lat, max_lat, f_lat=2, f
     pts[:, 0] = np.tile(lon_ax, nn_lat)
     pts[:, 1] = np.repeat(lat_ax, nn_lon)
     return pts, nn_lat, nn_lon
+
+
+def ref_gpu_available() -> bool:
+    return os.path.exists(os.path.join(HERE, "_ref_gpu", "libgridd_ref_sm100a.so"))
+
+
+class ReferenceGPU:
+    """The unmodified reference GPU code (kernels.cu + GridD.cu) compiled for sm_100a behind oracle/ref_gpu_shim.cu:
+    the secondary comparator (needs a CUDA device)."""
+
+    def __init__(self, z, min_lon, max_lon, min_lat, max_lat):
+        self.lib = C.CDLL(os.path.join(HERE, "_ref_gpu", "libgridd_ref_sm100a.so"))
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        self.n_lat, self.n_lon = z.shape
+        self.lib.refd_create.argtypes = [_dp, C.c_int, C.c_int] + [C.c_double] * 4
+        self.lib.refd_create.restype = C.c_void_p
+        self.lib.refd_destroy.argtypes = [C.c_void_p]
+        self.lib.refd_batch.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int64, _dp]
+        self.lib.refd_batch.restype = C.c_double
+        self.lib.refd_kernel_ms.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int64, C.c_int, _dp]
+        self.lib.refd_kernel_ms.restype = C.c_double
+        self.h = self.lib.refd_create(_ptr(z, _dp), self.n_lat, self.n_lon, min_lon, max_lon, min_lat, max_lat)
+        if not self.h:
+            raise RuntimeError("reference GridD could not be created")
+
+    def close(self):
+        if self.h:
+            self.lib.refd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def batch(self, method, pts):
+        """GridD::batch* end to end -> (depths, milliseconds as the drivers' chrono sees them)."""
+        pts = _as_points(pts)
+        out = np.empty(pts.shape[0], dtype=np.float64)
+        ms = self.lib.refd_batch(self.h, method, _ptr(pts, _dp), pts.shape[0], _ptr(out, _dp))
+        return out, ms
+
+    def kernel_ms(self, method, pts, reps=5):
+        """The reference kernel alone on resident buffers -> (depths, ms per launch)."""
+        pts = _as_points(pts)
+        out = np.empty(pts.shape[0], dtype=np.float64)
+        ms = self.lib.refd_kernel_ms(self.h, method, _ptr(pts, _dp), pts.shape[0], reps, _ptr(out, _dp))
+        return out, ms

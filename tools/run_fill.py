@@ -4,7 +4,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "auv-real-time-interpolation_b200", "python")); sys.path.insert(0, ROOT)
 import torch, auvi
-auvi.LIB_PATH = os.environ.get("AUVI_LIB", auvi.LIB_PATH)        # A/B runs of two builds on one box
+auvi.LIB_PATH = os.environ.get("AUVI_LIB", auvi.LIB_PATH)
+if "AUVI_LIB" in os.environ:                                    # an older build: bind only what it exports
+    import ctypes as _C; _l = _C.CDLL(auvi.LIB_PATH); auvi.SYMBOLS = {k: v for k, v in auvi.SYMBOLS.items() if hasattr(_l, k)}        # A/B runs of two builds on one box
 n = int(sys.argv[1]); frac = float(sys.argv[2]); methods = sys.argv[3].split(","); reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 dev = torch.device("cuda", 0)
 i = torch.arange(n, device=dev, dtype=torch.float64) * (100.0 / (n - 1))

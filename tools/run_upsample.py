@@ -4,6 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "auv-real-time-interpolation_b200", "python")); sys.path.insert(0, ROOT)
 import torch, auvi
 auvi.LIB_PATH = os.environ.get("AUVI_LIB", auvi.LIB_PATH)
+if "AUVI_LIB" in os.environ:                                    # an older build: bind only what it exports
+    import ctypes as _C; _l = _C.CDLL(auvi.LIB_PATH); auvi.SYMBOLS = {k: v for k, v in auvi.SYMBOLS.items() if hasattr(_l, k)}
 n = int(sys.argv[1]); dt = sys.argv[2]; cases = [tuple(int(v) for v in c.split("x")) for c in sys.argv[3].split(",")]
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6455.9) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6455.9
 tdt = torch.float32 if dt == "f32" else torch.float64
