@@ -292,3 +292,25 @@ class ReferenceGPU:
         out = np.empty(pts.shape[0], dtype=np.float64)
         ms = self.lib.refd_kernel_ms(self.h, method, _ptr(pts, _dp), pts.shape[0], reps, _ptr(out, _dp))
         return out, ms
+
+
+def hash_mask(row_lo, row_hi, n_lon, fraction, seed=42):
+    """Rows [row_lo,row_hi) of the counter-hash mask auvi_grid_mask_hash draws (csrc/ingest.cu mask_hash_kernel): cell
+    (r,c) is removed iff splitmix64(flat ^ seed*K) >> 11 < fraction * 2^53, flat = r*n_lon + c.  -> bool array."""
+    r = np.arange(row_lo, row_hi, dtype=np.uint64)[:, None]
+    c = np.arange(n_lon, dtype=np.uint64)[None, :]
+    with np.errstate(over="ignore"):
+        x = (r * np.uint64(n_lon) + c) ^ (np.uint64(seed) * np.uint64(0xD1342543DE82EF95))
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    f = min(max(float(fraction), 0.0), 1.0)
+    return (x >> np.uint64(11)) < np.uint64(int(f * 9007199254740992.0))
+
+
+def synth_rows(n_lat_global, n_lon, row_lo, row_hi):
+    """Rows [row_lo,row_hi) of the seamount field (generate_csv_grids.cpp:32-70) of an n_lat_global x n_lon grid, float64."""
+    i = np.arange(n_lon, dtype=np.float64) * (100.0 / (n_lon - 1))
+    j = np.arange(row_lo, row_hi, dtype=np.float64) * (100.0 / (n_lat_global - 1))
+    return -(10.0 + 2.0 * i)[None, :] + 100.0 * np.exp(-(((i - 75.0) ** 2)[None, :] + ((j - 50.0) ** 2)[:, None]) / 450.0)

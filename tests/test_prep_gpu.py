@@ -164,3 +164,28 @@ def test_csv_errors(auvi):
         auvi.Grid.from_csv(b"1,2\n3,abc\n", (0.0, 1.0, 0.0, 1.0))
     with pytest.raises(auvi.AuviError, match="not a number"):
         auvi.Grid.from_csv(b"1,,2\n3,4,5\n", (0.0, 1.0, 0.0, 1.0))             # empty field
+
+
+def test_hash_mask_restatement_equals_the_device_mask():
+    """oracle/binding.hash_mask (numpy) is what bench.py's CPU arm masks its window with: it must be the mask
+    auvi_grid_mask_hash draws on the device, for a whole grid and for a row slab of it (global flat index)."""
+    import auvi
+    from oracle import binding as ob
+    n_lat, n_lon = 300, 517
+    z = np.ones((n_lat, n_lon), dtype=np.float32)
+    g = auvi.Grid(z, 0.0, 1.0, 0.0, 1.0)
+    n_masked = g.mask_hash(0.7, seed=42)
+    dev = np.isnan(g.read())
+    want = ob.hash_mask(0, n_lat, n_lon, 0.7, 42)
+    assert np.array_equal(dev, want) and n_masked == int(want.sum())
+    g.close()
+    lib = auvi.load()
+    import ctypes as C
+    h = C.c_void_p()
+    slab = np.ones((50, n_lon), dtype=np.float32)
+    assert lib.auvi_grid_create_slab(slab.ctypes.data, auvi.F32, n_lat, n_lon, 100, 50, 0.0, 1.0, 0.0, 1.0, 0, C.byref(h)) == 0
+    assert lib.auvi_grid_mask_hash(h, 0.3, 7, None, None) == 0
+    got = np.empty((50, n_lon), dtype=np.float32)
+    assert lib.auvi_grid_read(h, 100, 150, got.ctypes.data) == 0
+    lib.auvi_grid_destroy(h)
+    assert np.array_equal(np.isnan(got), ob.hash_mask(100, 150, n_lon, 0.3, 7))
