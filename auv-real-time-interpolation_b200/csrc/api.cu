@@ -31,6 +31,7 @@
 using namespace auvi;
 
 namespace auvi { int set_error(const std::string& msg); }   // for the host-only translation units (prep.cpp)
+extern "C" int auvi_grid_fit_variogram(auvi_grid* g, double* out_c0_c1_range);
 
 namespace {
 
@@ -170,6 +171,9 @@ struct auvi_grid {
     std::map<long long, AxisOwned*> axes;             // key: which*2^40 + kind*2^32 + factor
     float last_ms = 0.f;
     int last_tma = 0;
+    // opt-in AUVI_KRIGING_FITTED: exponential model c0 + c1 * (1 - exp(-h / range)) fitted to this grid (or set by the caller)
+    bool vg_valid = false;
+    double vg_c0 = 0.0, vg_c1 = 0.0, vg_range = 0.0;
 };
 
 namespace {
@@ -186,7 +190,22 @@ int make_streams(auvi_grid* g) {
 
 int check_common(const auvi_grid* g, int method) {
     if (!g) return fail("null grid handle");
-    if (method < AUVI_BILINEAR || method > AUVI_BILINEAR_SEARCH) return fail("unknown interpolation method");
+    if (method < AUVI_BILINEAR || method > AUVI_KRIGING_FITTED) return fail("unknown interpolation method");
+    return 0;
+}
+
+// The descriptor and kernel method a C-ABI method runs with.  AUVI_KRIGING_FITTED is the kriging kernel on the grid's own
+// fitted model in covariance form (exact.cuh GridView::vg_*); the fit happens on first use.
+int resolve_method(auvi_grid* g, int method, GridDesc* d, int* kernel_method) {
+    *d = g->d;
+    *kernel_method = method;
+    if (method != AUVI_KRIGING_FITTED) return 0;
+    if (!g->vg_valid) {
+        double unused[3];
+        if (auvi_grid_fit_variogram(g, unused)) return 1;
+    }
+    d->vg_nugget = g->vg_c1; d->vg_sill = -g->vg_c1; d->vg_inv_range = 1.0 / g->vg_range; d->vg_diag = g->vg_c0 + g->vg_c1;
+    *kernel_method = AUVI_KRIGING;
     return 0;
 }
 
@@ -524,7 +543,10 @@ int auvi_interp_points_device(auvi_grid* g, int method, const void* dev_pts, int
     if ((dev_sel == nullptr) != (dev_found == nullptr)) return fail("dev_sel and dev_found go together");
     if (g->d.row0 != 0 || g->d.rows != g->d.n_lat) return fail("point-list mode needs the whole grid resident");
     AUVI_CUDA(cudaSetDevice(g->device));
-    cudaError_t e = launch_points(g->d, method, static_cast<const double*>(dev_pts), stride_bytes / 8, n,
+    GridDesc desc;
+    int km = method;
+    if (resolve_method(g, method, &desc, &km)) return 1;
+    cudaError_t e = launch_points(desc, km, static_cast<const double*>(dev_pts), stride_bytes / 8, n,
                                   dev_out_elev, dev_sel, dev_found, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail_cuda("point-list launch", e);
     g_launches.fetch_add(1);
@@ -551,6 +573,9 @@ static int interp_points_host(auvi_grid* g, int method, const void* host_pts, in
     if (g->d.row0 != 0 || g->d.rows != g->d.n_lat) return fail("point-list mode needs the whole grid resident");
     AUVI_CUDA(cudaSetDevice(g->device));
     if (ensure_point_staging(g)) return 2;
+    GridDesc desc;
+    int km = method;
+    if (resolve_method(g, method, &desc, &km)) return 1;
 
     const int64_t sd = stride_bytes / 8, od = out_stride_bytes / 8;
     const double* src = static_cast<const double*>(host_pts);
@@ -585,7 +610,7 @@ static int interp_points_host(auvi_grid* g, int method, const void* host_pts, in
         cudaStream_t st = g->st[b];
         AUVI_CUDA(cudaMemcpyAsync(g->d_in[b], pin, sizeof(double) * 2 * cnt, cudaMemcpyHostToDevice, st));
         AUVI_CUDA(cudaEventRecord(g->ev_k0[b], st));
-        cudaError_t e = launch_points(g->d, method, g->d_in[b], 2, cnt, g->d_out[b], nullptr, nullptr, st);
+        cudaError_t e = launch_points(desc, km, g->d_in[b], 2, cnt, g->d_out[b], nullptr, nullptr, st);
         if (e != cudaSuccess) return fail_cuda("point-list launch", e);
         g_launches.fetch_add(1);
         AUVI_CUDA(cudaEventRecord(g->ev_k1[b], st));
@@ -632,7 +657,10 @@ int auvi_lattice_device(auvi_grid* g, int method, int axis_kind, int f_lat, int 
     AxisOwned *lat = nullptr, *lon = nullptr;
     if (get_axis(g, 1, axis_kind, f_lat, &lat) || get_axis(g, 0, axis_kind, f_lon, &lon)) return 1;
     LaunchInfo info;
-    cudaError_t e = launch_lattice(g->d, method, lat->view(), lon->view(), row_begin, row_end, dev_out, out_ld,
+    GridDesc desc;
+    int km = method;
+    if (resolve_method(g, method, &desc, &km)) return 1;
+    cudaError_t e = launch_lattice(desc, km, lat->view(), lon->view(), row_begin, row_end, dev_out, out_ld,
                                    fill, dev_sel9, static_cast<cudaStream_t>(stream), &info);
     if (e == cudaErrorInvalidValue && (g->d.row0 != 0 || g->d.rows != g->d.n_lat))
         return fail("row range needs grid rows outside the resident slab (halo too small)");
@@ -779,6 +807,82 @@ int auvi_peer_close(void* ptr) {
         g_peer_base.erase(it);
     }
     AUVI_CUDA(cudaIpcCloseMemHandle(base));
+    return 0;
+}
+
+// ---- opt-in: fitted variogram ---------------------------------------------------------------
+// Exponential model gamma(h) = c0 + c1 * (1 - exp(-h / a)), h in degrees as in GridH.cpp:371-380, fitted to the empirical
+// semivariances of the grid at lags 1, 2, 4, 8 cells along both axes (device reduction: metrics.cu): for each candidate
+// range a = h_max * 2^(m-2), m = 0..9, weighted least squares in (c0, c1) with the pair counts as weights (c0 clamped at
+// 0, then least squares through the origin); the candidate with the smallest residual wins.  oracle: orc_fit_variogram.
+int auvi_variogram_fit_from_sums(const double* sums16, double lon_step, double lat_step, double* out3) {
+    double h[8], gam[8], w[8];
+    int n = 0;
+    double h_max = 0.0;
+    for (int a = 0; a < 2; ++a)
+        for (int l = 0; l < 4; ++l) {
+            const double ss = sums16[a * 8 + 2 * l], cnt = sums16[a * 8 + 2 * l + 1];
+            if (!(cnt > 0.0)) continue;
+            h[n] = static_cast<double>(1 << l) * std::fabs(a == 0 ? lon_step : lat_step);
+            gam[n] = ss / (2.0 * cnt);
+            w[n] = cnt;
+            if (h[n] > h_max) h_max = h[n];
+            ++n;
+        }
+    if (n < 2 || !(h_max > 0.0)) return fail("variogram fit: fewer than two lags have pairs of valid cells");
+    double best_r = 0.0, best[3] = {0.0, 0.0, 0.0};
+    bool have = false;
+    for (int m = 0; m < 10; ++m) {
+        const double a = h_max * std::ldexp(1.0, m - 2);
+        double sw = 0, sf = 0, sff = 0, sg = 0, sfg = 0;
+        double f[8];
+        for (int k = 0; k < n; ++k) {
+            f[k] = 1.0 - std::exp(-h[k] / a);
+            sw += w[k]; sf += w[k] * f[k]; sff += w[k] * f[k] * f[k]; sg += w[k] * gam[k]; sfg += w[k] * f[k] * gam[k];
+        }
+        const double det = sw * sff - sf * sf;
+        double c1 = det != 0.0 ? (sw * sfg - sf * sg) / det : 0.0;
+        double c0 = (sg - c1 * sf) / sw;
+        if (!(c0 >= 0.0) || det == 0.0) { c0 = 0.0; c1 = sff > 0.0 ? sfg / sff : 0.0; }
+        if (!(c1 > 0.0) || !std::isfinite(c1) || !std::isfinite(c0)) continue;
+        double r = 0.0;
+        for (int k = 0; k < n; ++k) { const double e = gam[k] - c0 - c1 * f[k]; r += w[k] * e * e; }
+        if (!have || r < best_r) { have = true; best_r = r; best[0] = c0; best[1] = c1; best[2] = a; }
+    }
+    if (!have) return fail("variogram fit: no candidate range gives a positive sill (constant grid?)");
+    out3[0] = best[0]; out3[1] = best[1]; out3[2] = best[2];
+    return 0;
+}
+
+int auvi_grid_fit_variogram(auvi_grid* g, double* out_c0_c1_range) {
+    if (!g) return fail("null grid handle");
+    if (!out_c0_c1_range) return fail("null output");
+    if (g->d.row0 != 0 || g->d.rows != g->d.n_lat)
+        return fail("the variogram fit needs the whole grid resident (on a row slab, pass the parameters with auvi_grid_set_variogram)");
+    AUVI_CUDA(cudaSetDevice(g->device));
+    void* scratch = nullptr;
+    const size_t bytes = (variogram_scratch_bytes() + 255) / 256 * 256 + 256;
+    AUVI_CUDA(cached_malloc(&scratch, bytes, g->device));
+    double* d_sums = reinterpret_cast<double*>(static_cast<char*>(scratch) + bytes - 256);
+    LaunchInfo info;
+    double sums[16];
+    cudaError_t e = launch_variogram_sums(g->d, scratch, d_sums, g->st[0], &info);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sums, d_sums, sizeof sums, cudaMemcpyDeviceToHost, g->st[0]);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g->st[0]);
+    if (e != cudaSuccess) { uncached_free(scratch); return fail_cuda("variogram sums", e); }
+    cached_free(scratch, bytes, g->device);
+    g_launches.fetch_add(info.launches);
+    double p[3];
+    if (auvi_variogram_fit_from_sums(sums, g->d.lon_step, g->d.lat_step, p)) return 1;
+    g->vg_c0 = p[0]; g->vg_c1 = p[1]; g->vg_range = p[2]; g->vg_valid = true;
+    out_c0_c1_range[0] = p[0]; out_c0_c1_range[1] = p[1]; out_c0_c1_range[2] = p[2];
+    return 0;
+}
+
+int auvi_grid_set_variogram(auvi_grid* g, double c0, double c1, double range) {
+    if (!g) return fail("null grid handle");
+    if (!(c0 >= 0.0) || !(c1 > 0.0) || !(range > 0.0)) return fail("variogram needs c0 >= 0, c1 > 0, range > 0");
+    g->vg_c0 = c0; g->vg_c1 = c1; g->vg_range = range; g->vg_valid = true;
     return 0;
 }
 

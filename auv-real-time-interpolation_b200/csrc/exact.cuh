@@ -16,7 +16,8 @@
 
 namespace auvi {
 
-enum Method : int { BILINEAR = 0, CUBIC = 1, KRIGING = 2, NN = 3, IDW = 4, BILINEAR_SEARCH = 5 };
+enum Method : int { BILINEAR = 0, CUBIC = 1, KRIGING = 2, NN = 3, IDW = 4, BILINEAR_SEARCH = 5, IDW_KNN = 6 };
+// (AUVI_KRIGING_FITTED = 7 is KRIGING evaluated with the grid's fitted variogram parameters: no method of its own here)
 
 constexpr int kMaxRadius = 10;   // GridH.cpp:275, :339
 constexpr int kMaxCand   = 45;   // 3 + 2*(2*10+1): the most the early-terminating search can hold
@@ -32,6 +33,11 @@ struct GridView {
     int row0;                    // first global row held in z
     double min_lon, max_lon, min_lat, max_lat;
     double lon_step, lat_step;   // (max-min)/(n-1), GridH.cpp:156-157 / GridD.cu:52-53
+    // matrix entry of the kriging system as a function of the separation h: nugget + sill * (1 - exp(-h * inv_range)).
+    // The reference's constants are 1, 100, 1/10 (its variogram, GridH.cpp:371-376).  The opt-in AUVI_KRIGING_FITTED puts
+    // the fitted model here in covariance form: entry = c1 * exp(-h / a) = c1 + (-c1) * (1 - exp(-h / a)), diagonal c0 + c1
+    double vg_nugget, vg_sill, vg_inv_range;
+    double vg_diag;              // diagonal of the kriging matrix: gamma(0) = the nugget in the reference (GridH.cpp:386-392)
 
     __device__ __forceinline__ double at(int j, int i) const {
         return static_cast<double>(__ldg(z + static_cast<int64_t>(j - row0) * ld + i));
@@ -225,8 +231,8 @@ __device__ __forceinline__ int round_centre(double c, int n) {
 // -expm1(-t): the Taylor polynomial (degree 7 below t = 2^-7, degree 11 below 2^-4: truncation < 1e-19 relative), else the
 // library expm1.  Against the reference's own rounding of exp(-t) near 1 this moves gamma by ~1e-14 and the kriging
 // prediction by < 1e-9 m (measured on every Grid-B fixture; tests hold kriging to 1e-6 m).
-__device__ __forceinline__ double variogram_sq(double h2) {
-    const double t = (h2 > 0.0 ? h2 * rsqrt(h2) : 0.0) * 0.1;      // h / range; h to ~1 ulp, far inside the tolerance
+__device__ __forceinline__ double variogram_sq(double h2, double nugget, double sill, double inv_range) {
+    const double t = (h2 > 0.0 ? h2 * rsqrt(h2) : 0.0) * inv_range; // h / range; h to ~1 ulp, far inside the tolerance
     double em1;                                                    // expm1(-t)
     if (t < 0.0078125) {                                           // bathymetry grids: t ~ 1e-4 .. 1e-3; degree 7: < 1e-19 relative
         double q = -1.0 / 5040.0;
@@ -253,7 +259,7 @@ __device__ __forceinline__ double variogram_sq(double h2) {
     } else {
         em1 = expm1(-t);
     }
-    return fma(-100.0, em1, 1.0);
+    return fma(-sill, em1, nugget);
 }
 
 // ---- ordinary kriging on the four picked cells, GridH.cpp:361-419 ----------------------------------
@@ -275,16 +281,16 @@ __device__ double kriging_from_picked(const GridView<T>& g, const Picked& p, dou
     double M[5][6];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-        M[a][a] = 1.0;
+        M[a][a] = g.vg_diag;                                       // gamma(0) = the nugget (1) in the reference
 #pragma unroll
         for (int b = a + 1; b < 4; ++b) {
             const double dx = px[a] - px[b], dy = py[a] - py[b];
-            M[a][b] = variogram_sq(fma(dx, dx, dy * dy));
+            M[a][b] = variogram_sq(fma(dx, dx, dy * dy), g.vg_nugget, g.vg_sill, g.vg_inv_range);
             M[b][a] = M[a][b];
         }
         M[a][4] = 1.0; M[4][a] = 1.0;
         const double dx = px[a] - lon, dy = py[a] - lat;           // raw query lon/lat, :380
-        M[a][5] = variogram_sq(fma(dx, dx, dy * dy));
+        M[a][5] = variogram_sq(fma(dx, dx, dy * dy), g.vg_nugget, g.vg_sill, g.vg_inv_range);
     }
     M[4][4] = 0.0; M[4][5] = 1.0;
     double inv[5];
@@ -353,6 +359,53 @@ __device__ __forceinline__ double idw_from_picked(const Picked& p, double x, dou
     return ref + static_cast<double>(__fdividef(num, den));
 }
 
+// ---- OPT-IN: IDW over the TRUE four nearest valid cells ---------------------------------
+// The reference's search stops at the first pass that brings its count to four (GridH.cpp:82,115), so its "four nearest"
+// are nearest only among an order-dependent, early-terminated candidate list.  This method scans
+// the whole radius-10 window in the same enumeration order WITHOUT the two early breaks and keeps the four smallest
+// distances, ties going to the candidate enumerated first (a stable selection; the reference's swap-based selection has
+// no meaning without its list).  Rings are left as soon as no farther cell can matter: a cell of ring r lies at
+// distance >= r - 1 from a query whose centre is round(x), round(y).  Weights as IDW.  oracle: orc_idw_knn.
+template <typename T>
+__device__ double exact_idw_knn(const GridView<T>& g, double x, double y, Picked* out_sel) {
+    const int ci = round_centre(x, g.n_lon), cj = round_centre(y, g.n_lat);
+    Picked p;
+    p.found = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { p.i[k] = -1; p.j[k] = -1; p.v[k] = qnan(); p.d[k] = __longlong_as_double(0x7ff0000000000000LL); }
+    auto visit = [&](int i, int j) {
+        const double v = g.at(j, i);
+        if (isnan(v)) return;
+        const double ddi = dsub(dadd(static_cast<double>(i), 0.5), x), ddj = dsub(dadd(static_cast<double>(j), 0.5), y);
+        const double d = dsqrt(dadd(dmul(ddi, ddi), dmul(ddj, ddj)));
+        ++p.found;
+        if (!(d < p.d[3])) return;                                 // not among the four; an equal distance came later: loses
+        int at = 3;
+        while (at > 0 && d < p.d[at - 1]) { p.d[at] = p.d[at - 1]; p.v[at] = p.v[at - 1]; p.i[at] = p.i[at - 1]; p.j[at] = p.j[at - 1]; --at; }
+        p.d[at] = d; p.v[at] = v; p.i[at] = i; p.j[at] = j;
+    };
+    visit(ci, cj);
+    for (int r = 1; r <= kMaxRadius; ++r) {
+        if (p.found >= 4 && p.d[3] <= static_cast<double>(r - 1)) break;   // every cell of rings >= r is at least r - 1 away
+        const bool top_ok = cj - r >= 0, bot_ok = cj + r < g.n_lat;
+        for (int dx = -r; dx <= r; ++dx) {
+            const int i = ci + dx;
+            if (i < 0 || i >= g.n_lon) continue;
+            if (top_ok) visit(i, cj - r);
+            if (bot_ok) visit(i, cj + r);
+        }
+        const bool lef_ok = ci - r >= 0, rig_ok = ci + r < g.n_lon;
+        for (int dy = -r + 1; dy <= r - 1; ++dy) {
+            const int j = cj + dy;
+            if (j < 0 || j >= g.n_lat) continue;
+            if (lef_ok) visit(ci - r, j);
+            if (rig_ok) visit(ci + r, j);
+        }
+    }
+    if (out_sel) *out_sel = p;
+    return p.found > 0 ? idw_from_picked(p, x, y) : qnan();
+}
+
 // ---- one query, any method --------------------------------------------------------------------------
 // lon/lat are the raw query coordinates; x/y their index-space images (precomputed by the caller so
 // that lattice kernels can take them from per-axis tables).  NaN x or y means out of bounds.
@@ -363,6 +416,7 @@ __device__ double interp_exact(const GridView<T>& g, int method, double lon, dou
     if (isnan(x) || isnan(y)) return qnan();
     if (method == BILINEAR) { if (sel) sel->found = -2; return exact_bilinear(g, x, y); }
     if (method == CUBIC) return exact_cubic(g, x, y, sel);
+    if (method == IDW_KNN) return exact_idw_knn(g, x, y, sel);
     if (method == BILINEAR_SEARCH) {
         // OPT-IN (not a reference method): bilinear wherever the reference's bilinear returns a
         // number; where it returns NaN (all four corners missing, GridH.cpp:186-198) the 4-nearest mean the bicubic

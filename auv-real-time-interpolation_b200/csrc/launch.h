@@ -23,6 +23,7 @@ struct GridDesc {
     int row0 = 0, rows = 0;        // slab held in z: global rows [row0, row0+rows)
     double min_lon = 0, max_lon = 0, min_lat = 0, max_lat = 0;
     double lon_step = 0, lat_step = 0;
+    double vg_nugget = 1.0, vg_sill = 100.0, vg_inv_range = 0.1, vg_diag = 1.0;   // what the kriging kernels use (GridH.cpp:371-376)
 };
 
 template <typename T>
@@ -32,6 +33,7 @@ inline GridView<T> make_view(const GridDesc& d) {
     v.n_lat = d.n_lat; v.n_lon = d.n_lon; v.ld = d.ld; v.row0 = d.row0;
     v.min_lon = d.min_lon; v.max_lon = d.max_lon; v.min_lat = d.min_lat; v.max_lat = d.max_lat;
     v.lon_step = d.lon_step; v.lat_step = d.lat_step;
+    v.vg_nugget = d.vg_nugget; v.vg_sill = d.vg_sill; v.vg_inv_range = d.vg_inv_range; v.vg_diag = d.vg_diag;
     return v;
 }
 
@@ -78,6 +80,12 @@ cudaError_t launch_metrics(const void* truth, const void* est, int dtype, int64_
 cudaError_t launch_metrics_masked(const void* masked, int64_t ld_m, const void* filled, int64_t ld_f, const void* truth,
                                   int64_t ld_t, int dtype, int64_t rows, int cols, void* scratch, double* result5,
                                   cudaStream_t st, LaunchInfo* info);
+
+// metrics.cu -- empirical semivariances of the grid for the fitted variogram (opt-in AUVI_KRIGING_FITTED): for the lags
+// 1, 2, 4, 8 cells along each axis, sums[16] = {sum of squared differences, pair count} x {lon lags, lat lags} over the
+// pairs of valid cells; deterministic two-stage reduction.  scratch: variogram_scratch_bytes().
+size_t variogram_scratch_bytes();
+cudaError_t launch_variogram_sums(const GridDesc& d, void* scratch, double* sums16, cudaStream_t st, LaunchInfo* info);
 
 // ingest.cu -- Grid-B data preparation on the device (decode a NetCDF variable, mask cells).
 cudaError_t launch_decode_raw(const void* raw, int nc_type, int big_endian, int flip_rows, double scale, double offset,

@@ -139,4 +139,80 @@ cudaError_t launch_metrics_masked(const void* masked, int64_t ld_m, const void* 
     return cudaGetLastError();
 }
 
+// ---- empirical semivariances for the fitted variogram (opt-in AUVI_KRIGING_FITTED) -------------
+// The reference hard-codes its variogram (nugget 1, sill 100, range 10 degrees: GridH.cpp:371-376).  The opt-in fits the
+// same exponential model to the grid itself.  This kernel delivers the data of that fit: for the lags k = 1, 2, 4, 8 cells
+// along each axis, the sum of squared differences and the number of pairs of VALID cells k apart.  One pass, each cell
+// reads its eight partners (L1/L2 hits); deterministic: fixed partition over kVgBlocks blocks, fixed reduction trees.
+// sums16 layout: [axis (0 lon, 1 lat)][lag index 0..3][0 sum of squares, 1 pair count].
+constexpr int kVgBlocks = 148 * 4;
+
+template <typename T>
+__global__ void __launch_bounds__(kMetBlock)
+variogram_partial_kernel(const T* __restrict__ z, int64_t ld, int rows, int n_lon, double* __restrict__ part) {
+    double acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+    const int64_t total = static_cast<int64_t>(rows) * n_lon;
+    for (int64_t c = static_cast<int64_t>(blockIdx.x) * kMetBlock + threadIdx.x; c < total; c += static_cast<int64_t>(gridDim.x) * kMetBlock) {
+        const int r = static_cast<int>(c / n_lon), i = static_cast<int>(c - static_cast<int64_t>(r) * n_lon);
+        const double v = static_cast<double>(__ldg(z + static_cast<int64_t>(r) * ld + i));
+        if (isnan(v)) continue;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const int k = 1 << l;
+            if (i + k < n_lon) {
+                const double w = static_cast<double>(__ldg(z + static_cast<int64_t>(r) * ld + i + k));
+                if (!isnan(w)) { const double d = v - w; acc[2 * l] = fma(d, d, acc[2 * l]); acc[2 * l + 1] += 1.0; }
+            }
+            if (r + k < rows) {
+                const double w = static_cast<double>(__ldg(z + static_cast<int64_t>(r + k) * ld + i));
+                if (!isnan(w)) { const double d = v - w; acc[8 + 2 * l] = fma(d, d, acc[8 + 2 * l]); acc[8 + 2 * l + 1] += 1.0; }
+            }
+        }
+    }
+    __shared__ double s[kMetBlock / 32][16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        double v = 0.0;
+        for (int w = 0; w < kMetBlock / 32; ++w) v += s[w][threadIdx.x];
+        part[static_cast<int64_t>(blockIdx.x) * 16 + threadIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kMetBlock)
+variogram_final_kernel(const double* __restrict__ part, int n_part, double* __restrict__ sums16) {
+    __shared__ double s[kMetBlock / 16][16];
+    const int k = threadIdx.x & 15, lane16 = threadIdx.x >> 4;   // 16 groups of 16 threads: thread (lane16, k) sums entry k
+    double v = 0.0;
+    for (int b = lane16; b < n_part; b += kMetBlock / 16) v += part[static_cast<int64_t>(b) * 16 + k];
+    s[lane16][k] = v;
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        double t = 0.0;
+        for (int w = 0; w < kMetBlock / 16; ++w) t += s[w][threadIdx.x];
+        sums16[threadIdx.x] = t;
+    }
+}
+
+size_t variogram_scratch_bytes() { return sizeof(double) * 16 * kVgBlocks; }
+
+cudaError_t launch_variogram_sums(const GridDesc& d, void* scratch, double* sums16, cudaStream_t st, LaunchInfo* info) {
+    double* part = static_cast<double*>(scratch);
+    if (d.dtype == DT_F64)
+        variogram_partial_kernel<double><<<kVgBlocks, kMetBlock, 0, st>>>(static_cast<const double*>(d.z), d.ld, d.rows, d.n_lon, part);
+    else
+        variogram_partial_kernel<float><<<kVgBlocks, kMetBlock, 0, st>>>(static_cast<const float*>(d.z), d.ld, d.rows, d.n_lon, part);
+    variogram_final_kernel<<<1, kMetBlock, 0, st>>>(part, kVgBlocks, sums16);
+    if (info) info->launches += 2;
+    return cudaGetLastError();
+}
+
 }  // namespace auvi

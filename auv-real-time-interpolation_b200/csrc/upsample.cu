@@ -488,7 +488,7 @@ static cudaError_t launch_lattice_t(const GridDesc& d, int method, const AxisTab
         if (method == BILINEAR) return launch_tiled<T, BILINEAR>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
         if (method == CUBIC) return launch_tiled<T, CUBIC>(d, lat, lon, row_begin, row_end, out, out_ld, st, info);
     }
-    if (!sel && (fill || method == KRIGING || method == NN || method == IDW)) {
+    if (!sel && method != IDW_KNN && (fill || method == KRIGING || method == NN || method == IDW)) {   // IDW_KNN: per-query path
         static const bool v0 = getenv("AUVI_FILL_V0") != nullptr;        // A-B measurements only
         if (!v0) return launch_fill(d, method, lat, lon, row_begin, row_end, out, out_ld, fill, st, info);
     }
@@ -497,7 +497,7 @@ static cudaError_t launch_lattice_t(const GridDesc& d, int method, const AxisTab
         return fill ? launch_exact<T, M, true>(d, lat, lon, row_begin, row_end, out, out_ld, sel, st, info)  \
                     : launch_exact<T, M, false>(d, lat, lon, row_begin, row_end, out, out_ld, sel, st, info);
     switch (method) {
-        AUVI_CASE(BILINEAR) AUVI_CASE(CUBIC) AUVI_CASE(KRIGING) AUVI_CASE(NN) AUVI_CASE(IDW) AUVI_CASE(BILINEAR_SEARCH)
+        AUVI_CASE(BILINEAR) AUVI_CASE(CUBIC) AUVI_CASE(KRIGING) AUVI_CASE(NN) AUVI_CASE(IDW) AUVI_CASE(BILINEAR_SEARCH) AUVI_CASE(IDW_KNN)
         default: return cudaErrorInvalidValue;
     }
 #undef AUVI_CASE

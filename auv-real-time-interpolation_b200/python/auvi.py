@@ -21,9 +21,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB_PATH = os.path.join(PKG, "lib", "libauvi.so")
 
-BILINEAR, CUBIC, KRIGING, NN, IDW, BILINEAR_SEARCH = 0, 1, 2, 3, 4, 5
+BILINEAR, CUBIC, KRIGING, NN, IDW, BILINEAR_SEARCH, IDW_KNN, KRIGING_FITTED = 0, 1, 2, 3, 4, 5, 6, 7
 METHOD_NAMES = {BILINEAR: "bilinear", CUBIC: "cubic", KRIGING: "kriging", NN: "nn", IDW: "idw",
-                BILINEAR_SEARCH: "bilinear_search"}
+                BILINEAR_SEARCH: "bilinear_search", IDW_KNN: "idw_knn", KRIGING_FITTED: "kriging_fitted"}
 F64, F32 = 0, 1
 AXIS_EXPANDED, AXIS_NODES = 0, 1
 
@@ -53,6 +53,9 @@ SYMBOLS = {
     "auvi_grid_mask_cells": (_i32, [_vp, _vp, _i64, _vp]),
     "auvi_grid_mask_hash": (_i32, [_vp, _dbl, C.c_uint64, C.POINTER(_i64), _vp]),
     "auvi_grid_read": (_i32, [_vp, _i64, _i64, _vp]),
+    "auvi_grid_fit_variogram": (_i32, [_vp, C.POINTER(_dbl)]),
+    "auvi_grid_set_variogram": (_i32, [_vp, _dbl, _dbl, _dbl]),
+    "auvi_variogram_fit_from_sums": (_i32, [C.POINTER(_dbl), _dbl, _dbl, C.POINTER(_dbl)]),
     "auvi_peer_export": (_i32, [_vp, _vp]),
     "auvi_peer_open": (_i32, [_vp, C.POINTER(_vp)]),
     "auvi_peer_close": (_i32, [_vp]),
@@ -193,6 +196,15 @@ class Grid:
         out = np.empty((row_end - row_begin, self.n_lon), dtype=_np_dtype(self.dtype))
         _check(load().auvi_grid_read(self._h, row_begin, row_end, out.ctypes.data))
         return out
+
+    def fit_variogram(self):
+        """-> (c0, c1, range) of the exponential variogram fitted to this grid (opt-in KRIGING_FITTED)."""
+        out3 = (_dbl * 3)()
+        _check(load().auvi_grid_fit_variogram(self._h, out3))
+        return out3[0], out3[1], out3[2]
+
+    def set_variogram(self, c0, c1, rng):
+        _check(load().auvi_grid_set_variogram(self._h, c0, c1, rng))
 
     def fill_metrics_device(self, filled_ptr, filled_ld, truth_ptr, truth_ld, row_begin, row_end, stream=None):
         """-> (mae, rmse, max, n_nan, n) over the cells that are NaN in this (masked) grid."""

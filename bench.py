@@ -566,7 +566,8 @@ def methods_mariana(c):
     d_truth = torch.from_numpy(case["truth"]).cuda()
     res = {}
     for name, meth in (("bilinear", auvi.BILINEAR), ("cubic", auvi.CUBIC), ("kriging", auvi.KRIGING),
-                       ("nn", auvi.NN), ("idw", auvi.IDW), ("bilinear_search(opt-in)", auvi.BILINEAR_SEARCH)):
+                       ("nn", auvi.NN), ("idw", auvi.IDW), ("bilinear_search(opt-in)", auvi.BILINEAR_SEARCH),
+                       ("idw_true_4_nearest(opt-in)", auvi.IDW_KNN), ("kriging_fitted_variogram(opt-in)", auvi.KRIGING_FITTED)):
         g.interp_points(meth, case["pts"])
         t0 = time.perf_counter()
         for _ in range(5):

@@ -26,7 +26,13 @@ typedef struct auvi_grid auvi_grid;   /* opaque: a depth grid (or a row slab of 
 enum { AUVI_BILINEAR = 0, AUVI_CUBIC = 1, AUVI_KRIGING = 2, AUVI_NN = 3, AUVI_IDW = 4,
        /* opt-in, changes results: bilinear, and where the reference's bilinear returns NaN (all four
         * corners missing, GridH.cpp:186-198) the ring-search 4-nearest mean of the bicubic fallback (GridH.cpp:272-318) */
-       AUVI_BILINEAR_SEARCH = 5 };
+       AUVI_BILINEAR_SEARCH = 5,
+       /* opt-in: IDW over the TRUE four nearest valid cells of the radius-10 window -- the reference's search without its two
+        * early `count >= 4` breaks (GridH.cpp:82,115), ties to the cell enumerated first */
+       AUVI_IDW_KNN = 6,
+       /* opt-in: ordinary kriging on the reference's four picks with the exponential variogram FITTED to the grid instead of
+        * the constants of GridH.cpp:371-376 (auvi_grid_fit_variogram; fitted on first use) */
+       AUVI_KRIGING_FITTED = 7 };
 /* Storage type of the depth grid and of lattice outputs. */
 enum { AUVI_F64 = 0, AUVI_F32 = 1 };
 /* How a lattice axis maps an output index to a coordinate:
@@ -165,6 +171,17 @@ int auvi_grid_mask_cells(auvi_grid* g, const int64_t* host_flat_idx, int64_t n, 
 int auvi_grid_mask_hash(auvi_grid* g, double fraction, uint64_t seed, int64_t* out_masked, void* stream);
 /* Copy grid rows [row_begin,row_end) back to a dense host array of the grid's dtype. */
 int auvi_grid_read(auvi_grid* g, int64_t row_begin, int64_t row_end, void* host_out);
+
+/* ---- Opt-in: fitted variogram (changes results, so never the default).  The model is
+ *      gamma(h) = c0 + c1 * (1 - exp(-h / range)), h in degrees as in GridH.cpp:371-380.  auvi_grid_fit_variogram reduces the
+ *      empirical semivariances of the grid at lags 1, 2, 4, 8 cells along both axes on the device and fits (c0, c1, range)
+ *      by weighted least squares over a ladder of candidate ranges; needs the whole grid resident.  A row slab takes the
+ *      parameters from auvi_grid_set_variogram.  AUVI_KRIGING_FITTED solves the kriging system in covariance form
+ *      (c1 * exp(-h / range) off the diagonal, c0 + c1 on it) on the same four cells the reference's search picks. ---- */
+int auvi_grid_fit_variogram(auvi_grid* g, double* out_c0_c1_range);      /* out: 3 doubles */
+int auvi_grid_set_variogram(auvi_grid* g, double c0, double c1, double range);
+/* Host only: the fit itself, from the 16 sums the device reduction delivers ([axis][lag 1,2,4,8][sum of squares, pairs]). */
+int auvi_variogram_fit_from_sums(const double* sums16, double lon_step, double lat_step, double* out_c0_c1_range);
 
 /* ---- Peer memory (one process per GPU): gather the row shards WITHOUT a collective.  The consumer exports its result
  *      buffer (any address inside a cudaMalloc allocation), producers map it and pass the mapped address as dev_out of

@@ -95,6 +95,38 @@ class Oracle:
         return tuple(getattr(self.lib, f)(_ptr(t, _dp), _ptr(e, _dp), n)
                      for f in ("orc_mae", "orc_rmse", "orc_maxerr"))
 
+    # ---- the opt-in methods (no reference code: checkers of our own definitions) ----
+    def batch_optin(self, method, pts, params=None, want_sel=False):
+        """method 6 = IDW over the true four nearest (no early break), 7 = kriging with params = (c0, c1, range)."""
+        pts = _as_points(pts)
+        n = pts.shape[0]
+        out = np.empty(n, dtype=np.float64)
+        sel = np.full((n, 4, 2), -1, dtype=np.int32) if want_sel else None
+        found = np.full(n, -1, dtype=np.int32) if want_sel else None
+        par = np.ascontiguousarray(params if params is not None else (0.0, 1.0, 1.0), dtype=np.float64)
+        self.lib.orc_batch_optin.argtypes = [C.POINTER(_OrcGrid), C.c_int, _dp, _dp, C.c_int64, _dp, _ip, _ip]
+        self.lib.orc_batch_optin.restype = C.c_int
+        rc = self.lib.orc_batch_optin(C.byref(self.g), method, _ptr(par, _dp), _ptr(pts, _dp), n, _ptr(out, _dp),
+                                      _ptr(sel, _ip), _ptr(found, _ip))
+        assert rc == 0
+        return (out, sel, found) if want_sel else out
+
+    def variogram_sums(self):
+        out = np.empty(16, dtype=np.float64)
+        self.lib.orc_variogram_sums.argtypes = [C.POINTER(_OrcGrid), _dp]
+        self.lib.orc_variogram_sums(C.byref(self.g), _ptr(out, _dp))
+        return out
+
+    def variogram_fit(self, sums=None):
+        """-> (c0, c1, range) of the exponential model fitted to this grid (orc_variogram_fit)."""
+        sums = self.variogram_sums() if sums is None else np.ascontiguousarray(sums, dtype=np.float64)
+        out = np.empty(3, dtype=np.float64)
+        self.lib.orc_variogram_fit.argtypes = [_dp, C.c_double, C.c_double, _dp]
+        self.lib.orc_variogram_fit.restype = C.c_int
+        rc = self.lib.orc_variogram_fit(_ptr(sums, _dp), self.g.lon_step, self.g.lat_step, _ptr(out, _dp))
+        assert rc == 0, "variogram fit failed"
+        return tuple(out)
+
 
 def node_axis(lo, hi, n):
     lib = C.CDLL(os.path.join(HERE, "liboracle.so"))

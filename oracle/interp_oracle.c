@@ -351,3 +351,184 @@ void orc_synth_grid(int n_lat, int n_lon, double* z) {
         }
     }
 }
+
+/* ==== OPT-IN METHODS -- no reference code; these are the checkers of our own definitions ==== */
+
+/* ---- IDW over the TRUE four nearest valid cells: the reference's enumeration (GridH.cpp:24-118) WITHOUT its two early
+ * `count >= 4` breaks (:82, :115), i.e. the whole radius-10 window, then the four smallest distances with ties going to
+ * the candidate enumerated first (a stable selection), then power-2 weights as orc_idw. ------------------------------ */
+#define ORC_FULL_CAND 441
+typedef struct { int i[ORC_FULL_CAND], j[ORC_FULL_CAND]; double v[ORC_FULL_CAND], d[ORC_FULL_CAND]; int n; } orc_full;
+
+static void consider_full(const orc_grid* g, int i, int j, double x, double y, orc_full* c) {
+    double v = cell(g, j, i);
+    if (isnan(v)) return;
+    double di = (i + 0.5) - x, dj = (j + 0.5) - y;
+    c->i[c->n] = i; c->j[c->n] = j; c->v[c->n] = v;
+    c->d[c->n] = sqrt(di * di + dj * dj);
+    ++c->n;
+}
+
+double orc_idw_knn(const orc_grid* g, double lon, double lat, int32_t* sel, int32_t* found) {
+    if (found) *found = -1;
+    if (sel) for (int k = 0; k < 8; ++k) sel[k] = -1;
+    if (outside(g, lon, lat)) return NAN;
+    double x = (lon - g->min_lon) / g->lon_step;
+    double y = (lat - g->min_lat) / g->lat_step;
+    int ci = clampi((int)round(x), 0, g->n_lon - 1);
+    int cj = clampi((int)round(y), 0, g->n_lat - 1);
+    orc_full c;
+    c.n = 0;
+    consider_full(g, ci, cj, x, y, &c);
+    for (int r = 1; r <= ORC_MAX_RADIUS; ++r) {           /* every ring, both passes, no early exit */
+        int top = cj - r, bot = cj + r;
+        for (int dx = -r; dx <= r; ++dx) {
+            int i = ci + dx;
+            if (i < 0 || i >= g->n_lon) continue;
+            if (top >= 0)        consider_full(g, i, top, x, y, &c);
+            if (bot < g->n_lat)  consider_full(g, i, bot, x, y, &c);
+        }
+        int lef = ci - r, rig = ci + r;
+        for (int dy = -r + 1; dy <= r - 1; ++dy) {
+            int j = cj + dy;
+            if (j < 0 || j >= g->n_lat) continue;
+            if (lef >= 0)        consider_full(g, lef, j, x, y, &c);
+            if (rig < g->n_lon)  consider_full(g, rig, j, x, y, &c);
+        }
+    }
+    /* NOTE: `found` of this method counts the candidates of the rings the device scans before it can stop; the oracle
+     * reports the picks only (found = min(n, 4) is what the tests compare). */
+    int m = c.n < 4 ? c.n : 4;
+    if (found) *found = m;
+    if (c.n == 0) return NAN;
+    int taken[4] = {-1, -1, -1, -1};
+    for (int p = 0; p < m; ++p) {                          /* stable selection: first strict minimum among the rest */
+        int best = -1;
+        for (int k = 0; k < c.n; ++k) {
+            if (k == taken[0] || k == taken[1] || k == taken[2] || k == taken[3]) continue;
+            if (best < 0 || c.d[k] < c.d[best]) best = k;
+        }
+        taken[p] = best;
+        if (sel) { sel[2 * p] = c.i[best]; sel[2 * p + 1] = c.j[best]; }
+    }
+    double num = 0.0, den = 0.0;
+    for (int p = 0; p < m; ++p) {
+        int k = taken[p];
+        if (c.d[k] == 0.0) return c.v[k];
+        double w = 1.0 / (c.d[k] * c.d[k]);
+        num += w * c.v[k];
+        den += w;
+    }
+    return num / den;
+}
+
+/* ---- fitted variogram: exponential model c0 + c1 * (1 - exp(-h / a)) from the grid's own empirical semivariances at lags
+ * 1, 2, 4, 8 cells along both axes.  sums16 layout as the device reduction: [axis 0 lon, 1 lat][lag][sum of squares, pairs].
+ * Fit = the library's auvi_variogram_fit_from_sums restated (weighted least squares over a ladder of candidate ranges). ---- */
+void orc_variogram_sums(const orc_grid* g, double* sums16) {
+    for (int k = 0; k < 16; ++k) sums16[k] = 0.0;
+    for (int r = 0; r < g->n_lat; ++r)
+        for (int i = 0; i < g->n_lon; ++i) {
+            double v = cell(g, r, i);
+            if (isnan(v)) continue;
+            for (int l = 0; l < 4; ++l) {
+                int k = 1 << l;
+                if (i + k < g->n_lon) { double w = cell(g, r, i + k); if (!isnan(w)) { sums16[2 * l] += (v - w) * (v - w); sums16[2 * l + 1] += 1.0; } }
+                if (r + k < g->n_lat) { double w = cell(g, r + k, i); if (!isnan(w)) { sums16[8 + 2 * l] += (v - w) * (v - w); sums16[8 + 2 * l + 1] += 1.0; } }
+            }
+        }
+}
+
+int orc_variogram_fit(const double* sums16, double lon_step, double lat_step, double* out3) {
+    double h[8], gam[8], w[8], h_max = 0.0;
+    int n = 0;
+    for (int a = 0; a < 2; ++a)
+        for (int l = 0; l < 4; ++l) {
+            double ss = sums16[a * 8 + 2 * l], cnt = sums16[a * 8 + 2 * l + 1];
+            if (!(cnt > 0.0)) continue;
+            h[n] = (double)(1 << l) * fabs(a == 0 ? lon_step : lat_step);
+            gam[n] = ss / (2.0 * cnt);
+            w[n] = cnt;
+            if (h[n] > h_max) h_max = h[n];
+            ++n;
+        }
+    if (n < 2 || !(h_max > 0.0)) return 1;
+    double best_r = 0.0;
+    int have = 0;
+    for (int m = 0; m < 10; ++m) {
+        double a = h_max * ldexp(1.0, m - 2), f[8];
+        double sw = 0, sf = 0, sff = 0, sg = 0, sfg = 0;
+        for (int k = 0; k < n; ++k) {
+            f[k] = 1.0 - exp(-h[k] / a);
+            sw += w[k]; sf += w[k] * f[k]; sff += w[k] * f[k] * f[k]; sg += w[k] * gam[k]; sfg += w[k] * f[k] * gam[k];
+        }
+        double det = sw * sff - sf * sf;
+        double c1 = det != 0.0 ? (sw * sfg - sf * sg) / det : 0.0;
+        double c0 = (sg - c1 * sf) / sw;
+        if (!(c0 >= 0.0) || det == 0.0) { c0 = 0.0; c1 = sff > 0.0 ? sfg / sff : 0.0; }
+        if (!(c1 > 0.0) || !isfinite(c1) || !isfinite(c0)) continue;
+        double r = 0.0;
+        for (int k = 0; k < n; ++k) { double e = gam[k] - c0 - c1 * f[k]; r += w[k] * e * e; }
+        if (!have || r < best_r) { have = 1; best_r = r; out3[0] = c0; out3[1] = c1; out3[2] = a; }
+    }
+    return have ? 0 : 1;
+}
+
+/* Ordinary kriging on the reference's four picks (same search, same selection as orc_kriging) with the fitted model in
+ * covariance form: C(h) = c1 * exp(-h / a) between distinct points and towards the query, c0 + c1 on the diagonal; the
+ * 5 x 5 system [C 1; 1' 0][w; mu] = [c; 1] solved by Gaussian elimination with partial pivoting (any exact solver will do). */
+double orc_kriging_fitted(const orc_grid* g, double lon, double lat, double c0, double c1, double a, int32_t* sel, int32_t* found) {
+    if (found) *found = -1;
+    if (sel) for (int k = 0; k < 8; ++k) sel[k] = -1;
+    if (outside(g, lon, lat)) return NAN;
+    orc_cands c;
+    int n = round_centre_search(g, lon, lat, &c, NULL, NULL);
+    if (found) *found = n;
+    if (n < 4) { export_sel(&c, sel); return mean_first(&c); }
+    pick_four(&c);
+    export_sel(&c, sel);
+    double px[4], py[4], M[5][6];
+    for (int k = 0; k < 4; ++k) {
+        px[k] = g->min_lon + (c.i[k] + 0.5) * g->lon_step;
+        py[k] = g->min_lat + (c.j[k] + 0.5) * g->lat_step;
+    }
+    memset(M, 0, sizeof M);
+    for (int p = 0; p < 4; ++p) {
+        for (int q = 0; q < 4; ++q) {
+            double dx = px[p] - px[q], dy = py[p] - py[q];
+            M[p][q] = p == q ? c0 + c1 : c1 * exp(-sqrt(dx * dx + dy * dy) / a);
+        }
+        M[p][4] = 1.0; M[4][p] = 1.0;
+        double dx = px[p] - lon, dy = py[p] - lat;
+        M[p][5] = c1 * exp(-sqrt(dx * dx + dy * dy) / a);
+    }
+    M[4][5] = 1.0;
+    for (int r = 0; r < 5; ++r) {
+        int piv = r;
+        for (int k = r + 1; k < 5; ++k) if (fabs(M[k][r]) > fabs(M[piv][r])) piv = k;
+        if (fabs(M[piv][r]) < 1e-300) return mean_valid4(c.v[0], c.v[1], c.v[2], c.v[3]);
+        if (piv != r) for (int q = 0; q < 6; ++q) { double t = M[r][q]; M[r][q] = M[piv][q]; M[piv][q] = t; }
+        for (int k = 0; k < 5; ++k) {
+            if (k == r) continue;
+            double f = M[k][r] / M[r][r];
+            for (int q = r; q < 6; ++q) M[k][q] -= f * M[r][q];
+        }
+    }
+    double out = 0.0;
+    for (int k = 0; k < 4; ++k) out += (M[k][5] / M[k][k]) * c.v[k];
+    return out;
+}
+
+/* batch forms of the opt-in methods: method 6 = IDW_KNN, 7 = KRIGING_FITTED (params = {c0, c1, range}) */
+int orc_batch_optin(const orc_grid* g, int method, const double* params, const double* pts, int64_t n, double* out,
+                    int32_t* sel, int32_t* found) {
+    for (int64_t k = 0; k < n; ++k) {
+        double lon = pts[3 * k], lat = pts[3 * k + 1];
+        int32_t* s = sel ? sel + 8 * k : NULL;
+        int32_t* f = found ? found + k : NULL;
+        if (method == 6) out[k] = orc_idw_knn(g, lon, lat, s, f);
+        else if (method == 7) out[k] = orc_kriging_fitted(g, lon, lat, params[0], params[1], params[2], s, f);
+        else return 1;
+    }
+    return 0;
+}
