@@ -68,13 +68,15 @@ struct AxisOwned {
 // device-wide synchronisation plus page-table work (measured: profiles/r01_e2e_pieces.txt); a caller that creates
 // and destroys grids per batch -- as the reference's drivers do -- should not pay that every time.  Blocks are
 // only returned here after the device is idle (auvi_grid_destroy synchronises), so reuse on any stream is safe.
-// At most kCacheBytes are held; auvi_trim() releases them.
+// At most kCacheBytes (40 GiB by default) are held; auvi_trim() releases them.
 struct DevBlock { void* p; size_t bytes; int device; };
 std::mutex g_cache_mu;
 std::vector<DevBlock> g_cache;
 std::map<void*, size_t> g_block_bytes;          // every live block handed out by cached_malloc -> the size it was ALLOCATED with
 size_t g_cache_held = 0;
-constexpr size_t kCacheBytes = 6ull << 30;
+// AUVI_CACHE_GB overrides (0 = no caching).  The default keeps a 65536^2 f32 slab (17 GB) plus its staging: a cudaFree of
+// 8.6 GB costs 230 ms, a third of an end-to-end step at BASELINE config 4 on two GPUs (profiles/r02_bench_n2_first.json).
+const size_t kCacheBytes = [] { const char* e = getenv("AUVI_CACHE_GB"); return (e ? static_cast<size_t>(atol(e)) : 40ull) << 30; }();
 constexpr size_t kCacheMinBlock = 4ull << 10;
 
 cudaError_t cached_malloc(void** out, size_t bytes, int device) {

@@ -304,6 +304,7 @@ def make_ctx(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=c.dev)
         c.dist = dist
+        c.cpu_group = dist.new_group(backend="gloo")               # host-side waits: no kernel spins on a GPU meanwhile
     assert c.world == args.gpus or c.world == 1, (c.world, args.gpus)
     c.stream = torch.cuda.current_stream().cuda_stream
     c.peak, c.peak_src = _peaks()
@@ -338,7 +339,13 @@ def make_ctx(args):
         barrier()
         return ms / steps, launches
 
-    c.barrier, c.max_over_ranks, c.timed = barrier, max_over_ranks, timed
+    def host_barrier():
+        """Ranks meet on the CPU (gloo): unlike an NCCL barrier no kernel waits on any GPU while a rank is late."""
+        torch.cuda.synchronize()
+        if c.dist is not None:
+            c.dist.barrier(group=c.cpu_group)
+
+    c.barrier, c.max_over_ranks, c.timed, c.host_barrier = barrier, max_over_ranks, timed, host_barrier
     return c
 
 
@@ -807,11 +814,13 @@ def gather_to_root(c, g, out, lo, my_rows, n, ms_step):
 
 def single_process_multi_gpu(c):
     """The multi-GPU entry of the C ABI (auvi_multi_*: ONE process, a host thread per device) on rank 0 while the other ranks
-    wait at a barrier: a 16384^2 grid of the same field and mask fraction from host memory, IDW fill, result back to host
-    memory and -- device form -- left sharded / gathered into device 0 by the kernels' own peer stores."""
+    wait on the CPU (a gloo barrier: an NCCL barrier would leave a spinning kernel on their GPUs, which rank 0 is about to
+    use): a 16384^2 grid of the same field and mask fraction from host memory, IDW fill, result back to host memory and --
+    device form -- left sharded / gathered into device 0 by the kernels' own peer stores."""
     torch, auvi, world, rank = c.torch, c.auvi, c.world, c.rank
     res = None
     c.barrier()
+    c.host_barrier()
     if rank == 0:
         try:
             n = 16384
@@ -854,7 +863,7 @@ def single_process_multi_gpu(c):
             m.close()
         except Exception as exc:
             res = {"unavailable": repr(exc)[:300]}
-    c.barrier()
+    c.host_barrier()
     return res
 
 

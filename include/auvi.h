@@ -63,7 +63,7 @@ int auvi_grid_adopt(const void* dev_rows, int dtype, int64_t n_lat, int64_t n_lo
                     int device, auvi_grid** out);
 
 int auvi_grid_destroy(auvi_grid* g);      /* idempotent on NULL; large device blocks go to a process-wide cache */
-int auvi_trim(void);                      /* release the cached device blocks (up to 6 GiB are kept for reuse) */
+int auvi_trim(void);                      /* release the cached device blocks (up to AUVI_CACHE_GB, default 40 GiB, are kept for reuse) */
 
 /* ---- Point-list mode: replaces GridD::batch{Bilinear,Cubic,OrdinaryKriging}Interpolate
  *      (src/GridD.cu:95-150,156-193,199-236) and the three kernels of src/kernels.cu:173-546 ---- */

@@ -97,8 +97,11 @@ def test_kriging_fitted_matches_its_oracle(auvi, name, frac):
 
 
 def test_optin_rmse_beside_the_reference_methods(auvi, capsys):
-    """Depth RMSE against the unmasked GEBCO truth on Mariana at 10 / 50 / 90 % removal: the opt-ins are there to be more
-    accurate than the methods whose semantics they relax.  Printed with -s; asserted only where the claim is robust."""
+    """Depth RMSE against the unmasked GEBCO truth on Mariana at 10 / 50 / 90 % removal, the opt-ins beside the methods whose
+    semantics they relax.  Reported, not asserted as an improvement: measured on B200 (profiles/r02_optin_rmse.txt) the
+    true four nearest are WORSE than the reference's early-terminated four at 10 % removal (53.4 m vs 47.6 m: with the
+    reference's +0.5 cell-centre convention the four nearest cells all lie on one side of a node query), and the fitted
+    variogram changes a four-point kriging estimate by centimetres."""
     rows = []
     for frac in (0.1, 0.5, 0.9):
         case = ob.masked_case("mariana", frac)
@@ -115,4 +118,4 @@ def test_optin_rmse_beside_the_reference_methods(auvi, capsys):
             print(f"\nmariana @{frac:.0%}: RMSE m  " + "  ".join(f"{k} {v:.3f}" for k, v in r.items()), end="")
         print()
     for frac, r in rows:
-        assert r["idw_knn"] < r["idw"], (frac, r)                    # the true four nearest beat the early-terminated four
+        assert all(np.isfinite(v) and 0 < v < 200 for v in r.values()), (frac, r)
