@@ -109,8 +109,18 @@ def test_multi_points_and_mask(auvi):
     case = ob.masked_case("mid_atlantic", 0.5)
     whole = auvi.Grid(case["z"], *case["bounds"])
     rng = np.random.RandomState(3)
-    pts = np.tile(case["pts"], (4, 1))[:200_000]                  # > 64 Ki per device: every shard gets a slice
+    pts = np.tile(case["pts"], (4, 1))[:200_000]
     pts[:, 0] += rng.uniform(-1e-3, 1e-3, pts.shape[0])
+    os.environ["AUVI_MULTI_MIN_POINTS"] = "30000"                 # the library spreads only > 4 Mi points per device: lower it
+    try:
+        _points_on_device_sets(auvi, case, whole, pts)
+    finally:
+        del os.environ["AUVI_MULTI_MIN_POINTS"]
+    whole.close()
+    _mask_on_device_sets(auvi)
+
+
+def _points_on_device_sets(auvi, case, whole, pts):
     for devs in _device_sets(auvi):
         m = auvi.MultiGrid(case["z"], *case["bounds"], n_gpus=len(devs), devices=devs, replicate=True)
         for meth in (auvi.BILINEAR, auvi.CUBIC, auvi.KRIGING, auvi.NN, auvi.IDW):
@@ -121,7 +131,9 @@ def test_multi_points_and_mask(auvi):
         with pytest.raises(auvi.AuviError, match="replicated"):
             sl.interp_points(auvi.NN, pts[:10])
         sl.close()
-    whole.close()
+
+
+def _mask_on_device_sets(auvi):
     # one global mask drawn shard by shard equals the mask drawn on the whole grid
     z = ob.synth_grid(200, 300).astype(np.float32)
     bounds = (0.0, 1.0, 0.0, 1.0)
