@@ -294,11 +294,7 @@ __device__ __forceinline__ bool near_query(FillSmem<T>& s, const FillParams<T>& 
     return true;
 }
 
-// COOP (A/B measurement only, AUVI_FILL_COOP=1, IDW f32 fill): the general path's selection and epilogue run
-// warp-cooperatively -- eight lanes per query, the candidate list spread over the lanes, four shuffle min-reductions with
-// the list position as tie-break (north_star's "warp-cooperative search with shuffle reductions") -- instead of one thread
-// per query.  Measured and rejected: DESIGN.md section 10, profiles/r02_fill_coop_ab.txt.
-template <typename T, int METHOD, bool FILL, bool COOP = false>
+template <typename T, int METHOD, bool FILL>
 __global__ void __launch_bounds__(kFThreads, 3)
 fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FillParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -608,7 +604,7 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     // ---- phase B, general path (as a function of the record): searches that leave the 5 x 5 block or hold more than
     // kFNear candidates.  Candidates in list order into a per-thread list in shared memory, the reference's selection
     // literally on it (squared distances, with the sqrt guard of each comparison), then the method.
-    auto general_query = [&](int q, bool enum_only) -> int {        // returns the candidate count (-1: structure mismatch) when enum_only
+    auto general_query = [&](int q) {
         const uint32_t rec = s.rec[q];
         const int k = s.reck[q];
         const int r_end = rec & 15, lr_end = (rec >> 4) & 1, n = (rec >> 5) & 31;
@@ -703,7 +699,6 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             }
         }
         // cnt == n by construction (phase A counted the same bits)
-        if (COOP && enum_only) return cnt == n ? cnt : -1;
         // -- the reference's partial selection sort with swaps (GridH.cpp:123-140) on squared distances.
         // NN only needs the first pick: pass 0 (with fewer than four candidates the oracle's "first strict
         // minimum" is the same scan); the other methods run the four passes when four candidates exist.
@@ -724,7 +719,7 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 lcode[m * kFThreads] = lcode[best * kFThreads]; lcode[best * kFThreads] = cm;
             }
         }
-        if (unsure) { to_literal(k); return 0; }
+        if (unsure) { to_literal(k); return; }
         if (cnt >= 4) {
             T v[4];
             double d2v[4];
@@ -748,75 +743,6 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             }
             __stcs(out_tile + lj * p.out_ld + li, finish_few<T, METHOD>(cnt, fv[0], fv[1], fv[2], fd[0], fd[1], fd[2]));
         }
-        return 0;
-    };
-
-    // ---- COOP (A/B only): one chunk of general-path records, selection + epilogue by eight lanes per query --------------
-    // Every lane first enumerates ITS query's candidates into its shared-memory list (as the per-thread path does).  Then, in
-    // eight rounds, the four 8-lane groups of the warp each take one query: lane s of the group holds list entries s and
-    // s + 8; a pass of the reference's selection (GridH.cpp:123-140) is a shuffle min-reduction over (distance, position) --
-    // smallest distance, earliest position: the first strict minimum -- followed by the swap of entry m with the winner,
-    // done between the two owning lanes.  Near ties (two different values within sqrt rounding) go to the literal path.
-    auto coop_general_chunk = [&](int q_first) {
-        const int q_mine = q_first + lane;
-        const bool have = q_mine < q_near;
-        const int my_cnt = have ? general_query(q_mine, true) : -1;
-        __syncwarp();
-        const uint32_t gmask = 0xFFu << (lane & 24);
-        const int gbase = lane & 24, sub = lane & 7;
-        const double inf = __longlong_as_double(0x7ff0000000000000LL);
-        for (int round = 0; round < 8; ++round) {
-            const int owner = round * 4 + (lane >> 3);               // the lane whose query this group works on
-            const int cnt = __shfl_sync(0xffffffffu, my_cnt, owner);
-            const int q = q_first + owner;
-            if (q >= q_near) continue;                              // group-uniform
-            const int k = s.reck[q];
-            if (cnt < 4) { if (sub == 0) to_literal(k); continue; } // out of rings / structure mismatch: rare, literal path
-            const int col = (tid & ~31) + owner;                    // the owner's list column
-            double d0 = sub < cnt ? s.d2[sub * kFThreads + col] : inf, d1 = sub + 8 < cnt ? s.d2[(sub + 8) * kFThreads + col] : inf;
-            int c0e = sub < cnt ? s.code[sub * kFThreads + col] : 0, c1e = sub + 8 < cnt ? s.code[(sub + 8) * kFThreads + col] : 0;
-            bool unsure = false;
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                double bd = inf;
-                int bp = 99;
-                if (sub >= m && d0 < bd) { bd = d0; bp = sub; }
-                if (d1 < bd) { bd = d1; bp = sub + 8; }
-#pragma unroll
-                for (int o = 1; o < 8; o <<= 1) {
-                    const double od = __shfl_xor_sync(gmask, bd, o);
-                    const int op = __shfl_xor_sync(gmask, bp, o);
-                    if (od < bd || (od == bd && op < bp)) { bd = od; bp = op; }
-                }
-                // a different value within sqrt rounding of the winner: the reference's comparison of square roots may tie
-                const bool u = (sub >= m && sub != bp && d0 != bd && dmul(d0, kSafeRatio) < bd) ||
-                               (sub + 8 != bp && d1 != bd && dmul(d1, kSafeRatio) < bd);
-                unsure |= (__ballot_sync(gmask, u) & gmask) != 0u;
-                // swap entry m (lane m of the group, slot 0) with the winner (lane bp & 7, slot bp >> 3)
-                const double dm = __shfl_sync(gmask, d0, gbase + m);
-                const int cm = __shfl_sync(gmask, c0e, gbase + m);
-                const int wc = __shfl_sync(gmask, bp >= 8 ? c1e : c0e, gbase + (bp & 7));
-                if (sub == (bp & 7)) { if (bp >= 8) { d1 = dm; c1e = cm; } else { d0 = dm; c0e = cm; } }
-                if (sub == m) { d0 = bd; c0e = wc; }
-            }
-            if (unsure) { if (sub == 0) to_literal(k); continue; }
-            // lanes 0..3 of the group hold the four picks in order: each fetches its value, the leader finishes
-            const int lj = k / kFW, li = k % kFW;
-            const int cig = s.cx[li], cjg = s.cy[lj];
-            const int dx = (c0e & 31) - 10, dy = (c0e >> 5) - 10;
-            const T myv = sub < 4 ? s.tile[(cjg - r0 + dy) * kFBW + (cig - c0) + dx] : static_cast<T>(0);
-            T v[4];
-            double d2v[4];
-            int pi[4], pj[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                v[e] = __shfl_sync(gmask, myv, gbase + e);
-                d2v[e] = __shfl_sync(gmask, d0, gbase + e);
-                const int ce = __shfl_sync(gmask, c0e, gbase + e);
-                pi[e] = cig + (ce & 31) - 10; pj[e] = cjg + (ce >> 5) - 10;
-            }
-            if (sub == 0) __stcs(out_tile + lj * p.out_ld + li, finish_four<T, METHOD>(p, v, d2v, pi, pj, I0 + li, J0 + lj));
-        }
     };
 
     // ---- phase B: warps draw chunks of 32 records from a CTA-wide counter ------------------------------------------------
@@ -832,8 +758,7 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             if (ch >= all_chunks) break;
             if (ch < gen_chunks) {
                 const int q = ch * 32 + lane;
-                if (COOP) coop_general_chunk(ch * 32);
-                else if (q < q_near) general_query(q, false);
+                if (q < q_near) general_query(q);
                 __syncwarp();
                 continue;
             }
@@ -1094,10 +1019,6 @@ static cudaError_t launch_fill_t(const GridDesc& d, const AxisTables& lat, const
         memset(&tmap, 0, sizeof tmap);
         p.use_tma = make_grid_tensor_map(d, kFBW, kFBH, &tmap, /*nan_fill=*/true) ? 1 : 0;
         auto kern = fill_tiled_kernel<T, METHOD, FILL>;
-        if constexpr (METHOD == IDW && FILL && sizeof(T) == 4) {
-            static const bool coop = getenv("AUVI_FILL_COOP") != nullptr;   // A/B measurement of the cooperative general path
-            if (coop) kern = fill_tiled_kernel<T, METHOD, FILL, true>;
-        }
         const size_t smem = sizeof(FillSmem<T>);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;

@@ -96,13 +96,7 @@ __device__ __noinline__ T lattice_cell_exact(const TileParams<T>* p, int64_t J, 
 // columns (one 16-byte vector store per output row); a row group sweeps its half of the tile's rows
 // top to bottom, keeping the horizontal pass of the TAPS input rows under the current output row in
 // registers and sliding that window as the (group-uniform) latitude table advances.
-// STRIDED = false: a column thread owns COLS ADJACENT output columns and emits one 16-byte store per output row; its tap
-// loads from shared memory are then f_lon/COLS... apart between adjacent lanes -- conflict-free only when the longitude factor
-// is >= COLS.  STRIDED = true (picked by the host for small longitude factors): the thread owns columns ct, ct + 128, ... --
-// adjacent lanes read adjacent (or the same) shared-memory words whatever the factor, and each output row leaves as COLS
-// coalesced 4- / 8-byte stores.  (ncu, f32 bicubic 2x2: 97.7 M bank conflicts for 646 M warp instructions with adjacent
-// ownership: profiles/r02_ncu_upsample_small_factor.txt.)
-template <typename T, int METHOD, bool STRIDED>
+template <typename T, int METHOD>
 __global__ void __launch_bounds__(kTileThreads, sizeof(T) == 4 ? 4 : 3)
 upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileParams<T> p) {
     constexpr bool kCubic = (METHOD == CUBIC);
@@ -176,23 +170,16 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
         }
     }
     const int ct = tid % kColThreads, rg = tid / kColThreads;
-    // output column of this thread's c-th column, relative to the tile
-    auto tile_col = [&](int c) -> int { return STRIDED ? c * kColThreads + ct : ct * COLS + c; };
-    const int Ic = I0 + tile_col(0);                               // first (lowest) of this thread's columns
-    const T* col_tile[STRIDED ? COLS : 1];                         // the box each column reads from (column slabs)
+    const int Ic = I0 + ct * COLS;                                 // first of this thread's columns
+    const int my_slab = ct / (kColThreads / S);
+    const int c0 = slab_c0(my_slab);                               // this thread's box
+    const T* const my_tile = tile + my_slab * box_stride;
     int ox[COLS];
     double txd[COLS];
     float wx[kF64 ? 1 : COLS][4];
-    if constexpr (!STRIDED) {
-        const int my_slab = ct / (kColThreads / S);
-        col_tile[0] = tile + my_slab * box_stride;
-    }
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
-        const int I = I0 + tile_col(c);
-        const int sl = tile_col(c) / slab_cols;                    // this column's slab
-        const int c0 = slab_c0(sl);
-        if constexpr (STRIDED) col_tile[c] = tile + sl * box_stride;
+        const int I = Ic + c;
         double px = 0.0;
         int bx = c0 + LO;
         if (I < W) { px = __ldg(p.lon.pos + I); bx = __ldg(p.lon.base + I); }
@@ -231,18 +218,18 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     const int per_group = (nJ + kRowGroups - 1) / kRowGroups;
     const int jr_begin = rg * per_group, jr_end = min(nJ, jr_begin + per_group);
     if (jr_begin >= jr_end) return;
-    const bool full = !STRIDED && p.vec_ok && (Ic + COLS <= W);
-    T* out_row = p.out + (J0 - p.row_begin + jr_begin) * p.out_ld + I0;   // tile column 0 of the current output row
+    const bool full = p.vec_ok && (Ic + COLS <= W);
+    T* out_row = p.out + (J0 - p.row_begin + jr_begin) * p.out_ld + Ic;
     const int64_t out_ld = p.out_ld;
 
     // ---- horizontal pass of one tile row for this thread's columns --------------------------------
     // A NaN anywhere in a footprint (or a NaN weight: out of bounds) surfaces in the horizontal pass
     // of some row the output uses, so it is enough to probe those (cheaper than probing every output).
     T probe = 0;
-    auto hrow = [&](int row_off, T (&dst)[COLS]) {               // row_off = tile row * bw
+    auto hrow = [&](const T* r, T (&dst)[COLS]) {
 #pragma unroll
         for (int c = 0; c < COLS; ++c) {
-            const T* q = col_tile[STRIDED ? c : 0] + row_off + ox[c];
+            const T* q = r + ox[c];
             if constexpr (kF64) {
                 if constexpr (kCubic) dst[c] = catmull_rom_exact(q[0], q[1], q[2], q[3], txd[c]);
                 else dst[c] = dadd(dmul(dsub(1.0, txd[c]), q[0]), dmul(txd[c], q[1]));
@@ -277,11 +264,11 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
             }
         }
         if (full) {
-            store_stream_vec(out_row + ct * COLS, v);
+            store_stream_vec(out_row, v);
         } else {
 #pragma unroll
             for (int c = 0; c < COLS; ++c)
-                if (I0 + tile_col(c) < W) store_stream<T>(out_row + tile_col(c), v[c]);
+                if (Ic + c < W) store_stream<T>(out_row + c, v[c]);
         }
         out_row += out_ld;
     };
@@ -289,7 +276,7 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     T h[TAPS][COLS];
     int jr = jr_begin;
     int top = s_top[jr];                                           // window = tile rows [top, top+TAPS)
-    int next_row = top * bw;
+    const T* next_row = my_tile + top * bw;
 #pragma unroll
     for (int k = 0; k < TAPS; ++k, next_row += bw) hrow(next_row, h[k]);
 #pragma unroll 1
@@ -314,13 +301,12 @@ swept:
     // and replace every NaN by the exact per-query evaluation (ring-search fallbacks, NaN-corner
     // means, out-of-bounds NaN).  Kept out of the streaming loop so that the call and its local
     // arrays do not cost the clean path registers.
-    out_row = p.out + (J0 - p.row_begin + jr_begin) * p.out_ld + I0;
+    out_row = p.out + (J0 - p.row_begin + jr_begin) * p.out_ld + Ic;
     for (int jr = jr_begin; jr < jr_end; ++jr, out_row += p.out_ld) {
 #pragma unroll 1
         for (int c = 0; c < COLS; ++c) {
-            const int tc = tile_col(c);
-            if (I0 + tc >= W) break;
-            if (isnan(out_row[tc])) store_stream<T>(out_row + tc, lattice_cell_exact<T, METHOD>(&p, J0 + jr, I0 + tc));
+            if (Ic + c >= W) break;
+            if (isnan(out_row[c])) store_stream<T>(out_row + c, lattice_cell_exact<T, METHOD>(&p, J0 + jr, Ic + c));
         }
     }
 }
@@ -463,11 +449,7 @@ static cudaError_t launch_tiled(const GridDesc& d, const AxisTables& lat, const 
     p.use_tma = make_grid_tensor_map(d, bw, bh, &tmap) ? 1 : 0;
 
     const size_t smem = static_cast<size_t>(slabs) * p.box_stride * es;
-    // column ownership: strided when adjacent ownership would bank-conflict (longitude factor below the columns per thread)
-    const int f_lon = d.n_lon > 1 ? (lon.n - 1) / (d.n_lon - 1) : 1;
-    static const int force = [] { const char* e = getenv("AUVI_UPSAMPLE_STRIDED"); return e ? atoi(e) : -1; }();   // A/B only
-    const bool strided = force >= 0 ? force != 0 : f_lon < align;
-    auto kern = strided ? upsample_tiled_kernel<T, METHOD, true> : upsample_tiled_kernel<T, METHOD, false>;
+    auto kern = upsample_tiled_kernel<T, METHOD>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;

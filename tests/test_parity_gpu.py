@@ -722,43 +722,3 @@ def test_adopted_grid_with_unaligned_pitch_takes_the_plain_load_path(auvi, torch
             assert float((u[ok].double() - v[ok].double()).abs().max()) <= 1e-3 + 1e-5 * 4000
         assert bool((u[:, cols:] == 7.0).all())                     # the padding of the output rows is untouched
     g.close()
-
-
-@pytest.mark.parametrize("strided", ["0", "1"])
-def test_upsample_column_ownership_variants(strided):
-    """upsample_tiled_kernel has two column-ownership layouts (adjacent columns per thread + 16-byte stores, or strided
-    columns + coalesced scalar stores); the host picks by longitude factor.  AUVI_UPSAMPLE_STRIDED forces one of them for
-    every factor (read once per process, hence the child process): each must equal the per-query exact path -- bit for
-    bit on FP64 grids, within the FP32 tap-weight tolerance on FP32 grids -- at factors on both sides of the switch."""
-    import subprocess
-    code = r'''
-import sys, numpy as np, torch
-sys.path.insert(0, "auv-real-time-interpolation_b200/python"); sys.path.insert(0, ".")
-import auvi
-for dt, tdt in ((auvi.F32, torch.float32), (auvi.F64, torch.float64)):
-    n_lat, n_lon = 211, 1543
-    jj = torch.arange(n_lat, device="cuda", dtype=torch.float64)[:, None]; ii = torch.arange(n_lon, device="cuda", dtype=torch.float64)[None, :]
-    z = (-3000.0 + 700.0 * torch.sin(ii * 0.02) * torch.cos(jj * 0.03) + 0.5 * ii).to(tdt).contiguous()
-    z[50:53, 700:705] = float("nan")
-    g = auvi.Grid(adopt=dict(ptr=z.data_ptr(), dtype=dt, n_lat=n_lat, n_lon=n_lon, ld=n_lon, row0=0, rows=n_lat, keep=z), min_lon=10.0, max_lon=12.0, min_lat=50.0, max_lat=51.0)
-    st = torch.cuda.current_stream().cuda_stream
-    for fl, fo in ((1, 1), (2, 2), (4, 1), (1, 4), (3, 3), (4, 4)):
-        rows, cols = fl * (n_lat - 1) + 1, fo * (n_lon - 1) + 1
-        ld = (cols + 3) // 4 * 4
-        for meth in (auvi.BILINEAR, auvi.CUBIC):
-            u = torch.full((rows, ld), 7.0, dtype=tdt, device="cuda"); v = torch.full_like(u, 7.0)
-            sel = torch.empty((rows * cols, 9), dtype=torch.int32, device="cuda")
-            g.lattice_device(meth, auvi.AXIS_EXPANDED, fl, fo, 0, 0, rows, u.data_ptr(), ld, None, st)
-            g.lattice_device(meth, auvi.AXIS_EXPANDED, fl, fo, 0, 0, rows, v.data_ptr(), ld, sel.data_ptr(), st)
-            torch.cuda.synchronize()
-            assert torch.equal(torch.isnan(u), torch.isnan(v)), (dt, fl, fo, meth)
-            ok = ~torch.isnan(u)
-            if dt == auvi.F64: assert torch.equal(u[ok], v[ok]), (fl, fo, meth)
-            else: assert float((u[ok].double() - v[ok].double()).abs().max()) <= 1e-3 + 1e-5 * 4000, (fl, fo, meth)
-            assert bool((u[:, cols:] == 7.0).all())
-    g.close()
-print("variants ok")
-'''
-    env = dict(os.environ, AUVI_UPSAMPLE_STRIDED=strided)
-    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0 and "variants ok" in out.stdout, out.stdout[-1500:] + out.stderr[-3000:]
