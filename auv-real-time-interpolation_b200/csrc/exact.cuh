@@ -62,6 +62,22 @@ __device__ __forceinline__ double to_index_space(double c, double lo, double ste
     return ddiv(dsub(c, lo), step);
 }
 
+// s / n for n in 1..4, bit-identical to the IEEE division the reference performs (`sum / count`, GridH.cpp:17), without the
+// ~40-instruction FP64 division sequence: n = 1, 2, 4 are exact scalings (RN(s/4) and RN(s * 0.25) round the same real
+// number); n = 3 is one Markstein correction step on the correctly rounded reciprocal -- q = RN(s * y), r = s - 3q (exact in
+// an FMA), q' = RN(q + r * y) is the correctly rounded quotient (checked against the division on 3e8 values, incl. the
+// neighbours of multiples of three).  Outside the exponent range where q or r could go subnormal: the division itself.
+__device__ __forceinline__ double div_count(double s, int n) {
+    if (n == 3) {
+        const double y = 0.33333333333333331;                      // RN(1/3)
+        const double q = dmul(s, y);
+        const double r = fma(-3.0, q, s);
+        const double a = fabs(s);
+        return (a > 1e-280 && a < 1e300) ? fma(r, y, q) : ddiv(s, 3.0);
+    }
+    return dmul(s, n == 1 ? 1.0 : (n == 2 ? 0.5 : 0.25));
+}
+
 // Mean of the non-NaN members of four values, summed a,b,c,d in order (GridH.cpp:10-18).
 __device__ __forceinline__ double mean_valid4(double a, double b, double c, double d) {
     double s = 0.0; int n = 0;
@@ -69,7 +85,7 @@ __device__ __forceinline__ double mean_valid4(double a, double b, double c, doub
     if (!isnan(b)) { s = dadd(s, b); ++n; }
     if (!isnan(c)) { s = dadd(s, c); ++n; }
     if (!isnan(d)) { s = dadd(s, d); ++n; }
-    return n ? ddiv(s, static_cast<double>(n)) : qnan();
+    return n ? div_count(s, n) : qnan();
 }
 
 // ---- bilinear, GridH.cpp:160-210 ----------------------------------------------------------------
@@ -181,7 +197,7 @@ __device__ __forceinline__ void gather_picked(const GridView<T>& g, int ci, int 
 __device__ __forceinline__ double mean_found(const Picked& p) {
     double s = 0.0;
     for (int k = 0; k < p.found && k < 4; ++k) s = dadd(s, p.v[k]);
-    return p.found > 0 ? ddiv(s, static_cast<double>(p.found)) : qnan();
+    return p.found > 0 ? div_count(s, p.found < 4 ? p.found : 4) : qnan();
 }
 
 template <typename T>

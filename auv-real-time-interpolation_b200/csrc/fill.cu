@@ -191,7 +191,7 @@ __device__ __forceinline__ T finish_four(const FillParams<T>& p, const T (&v)[4]
         // fallbackAverage (GridH.cpp:10-18) of four numbers: ((0 + a) + b + c + d) / 4
         const double sum = dadd(dadd(dadd(dadd(0.0, static_cast<double>(v[0])), static_cast<double>(v[1])),
                                      static_cast<double>(v[2])), static_cast<double>(v[3]));
-        return static_cast<T>(ddiv(sum, 4.0));
+        return static_cast<T>(dmul(sum, 0.25));                     // == sum / 4, bit for bit
     }
     if (METHOD == IDW) {
         // FP32 weights 1/d^2 through the SFU reciprocal; values centred on the first pick (== exact.cuh idw_from_picked)
