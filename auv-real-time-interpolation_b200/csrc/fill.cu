@@ -62,8 +62,8 @@ constexpr int kFReplayMax = 256;                // near-tie queries replayed wit
 constexpr int kFSq = 3;                        // squared-offset tables cover |offset| <= kFSq
 constexpr int kFNear = 8;                      // near path: at most this many candidates, all within the 5 x 5 block
 constexpr int kFUnroll = 3;                    // rings unrolled with their row windows in registers; further rings: rolled loops
-constexpr int kFBinNear = 80;                  // bins 0..79: general path (termination x count); 80..84: near path by count
-constexpr int kFBins = 96;
+constexpr int kFBinNear = 110;                 // bins 0..109: general path (termination x count); 110..114: near path by count
+constexpr int kFBins = 128;                    // (the bin travels in 7 bits of a record; 127 is reserved)
 
 // 5 x 5 block around the search centre as one word whose bit order IS the reference's enumeration order
 // (GridH.cpp:36-117): bit 0 the centre; 1..6 ring-1 top/bottom rows (per column left to right: top, bottom);
@@ -551,7 +551,9 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         }
         if (n > kFNMax) to_literal(k);
         else {
-            const int tcode = r_end <= 3 ? (r_end - 1) * 2 + lr_end : 6;
+            // rings 1..5 each get bins of their own (round 2: with rings >= 4 lumped together, a warp of a 90 % masked tile mixed
+            // searches of 4, 5 and 6 rings: -4.5 % at 90 %, -11 % at 97 %, +0.5 % at 70 %: profiles/r02_fill_bins_ab.txt)
+            const int tcode = r_end <= 5 ? (r_end - 1) * 2 + lr_end : 10;
             const int ncls = n < 4 ? 9 : n - 4;                     // n in 4..12 -> 0..8
             const int bin = tcode * 10 + ncls;
             atomicAdd(&s.hist[bin], 1);
