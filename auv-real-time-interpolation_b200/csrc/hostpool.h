@@ -13,9 +13,11 @@
 #include <cstdlib>
 #include <functional>
 #include <mutex>
+#include <new>
 #include <thread>
 #include <vector>
 
+#include <pthread.h>
 #include <sched.h>
 
 namespace auvi {
@@ -95,6 +97,18 @@ class HostPool {
             if (n > 16) n = 16;
         }
         n_ = n < 1 ? 1 : (n > 64 ? 64 : n);
+        pthread_atfork(nullptr, nullptr, &HostPool::forget_workers_in_child);
+    }
+    // A forked child has this object but none of its threads: forget them, the next job spawns new ones.
+    static void forget_workers_in_child() {
+        HostPool& p = get();
+        for (std::thread& t : p.workers_) new (&t) std::thread();      // the handles belong to threads of the parent
+        p.workers_.clear();
+        for (Mailbox& b : p.box_) b.go.store(0, std::memory_order_relaxed);
+        p.pending_.store(0, std::memory_order_relaxed);
+        p.sleepers_.store(0, std::memory_order_relaxed);
+        p.gen_ = 0;
+        p.job_ = nullptr;
     }
     void spawn_locked() {
         while (static_cast<int>(workers_.size()) < n_ - 1) {
