@@ -61,6 +61,7 @@ SYMBOLS = {
     "auvi_peer_close": (_i32, [_vp]),
     "auvi_multi_create": (_i32, [_vp, _i32, _i64, _i64, _dbl, _dbl, _dbl, _dbl, _i32, _vp, _i32, C.POINTER(_vp)]),
     "auvi_multi_destroy": (_i32, [_vp]),
+    "auvi_multi_plan": (_i32, [_i64, _i32, _i32, _i32, _i32, C.POINTER(_i64)]),
     "auvi_multi_count": (_i32, [_vp]),
     "auvi_multi_shard": (_i32, [_vp, _i32, _i32, C.POINTER(_i32), C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),
     "auvi_multi_mask_hash": (_i32, [_vp, _dbl, C.c_uint64]),
@@ -299,6 +300,13 @@ def error_metrics_device(truth_ptr, est_ptr, dtype, n, stream=None):
     nn = _i64()
     _check(load().auvi_error_metrics_device(truth_ptr, est_ptr, dtype, n, out3, C.byref(nn), stream))
     return out3[0], out3[1], out3[2], nn.value
+
+
+def multi_plan(n_lat, n_gpus, k, f_lat=1, replicate=False):
+    """-> dict(own_lo, own_hi, in_lo, in_hi, row_lo, row_hi): the row plan of shard k (host only)."""
+    out = (_i64 * 6)()
+    _check(load().auvi_multi_plan(n_lat, n_gpus, k, f_lat, 1 if replicate else 0, out))
+    return dict(zip(("own_lo", "own_hi", "in_lo", "in_hi", "row_lo", "row_hi"), list(out)))
 
 
 class MultiGrid:

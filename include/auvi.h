@@ -204,6 +204,9 @@ typedef struct auvi_multi auvi_multi;
 int auvi_multi_create(const void* host_rowmajor, int dtype, int64_t n_lat, int64_t n_lon, double min_lon, double max_lon,
                       double min_lat, double max_lat, int n_gpus, const int* devices, int replicate, auvi_multi** out);
 int auvi_multi_destroy(auvi_multi* m);
+/* Host only (no GPU needed): the row plan auvi_multi_create uses for shard k of n_gpus.  out6 = {own_lo, own_hi, in_lo, in_hi,
+ * row_lo, row_hi}: grid rows owned, grid rows held (own + 14-row halo; all rows when replicated), lattice rows produced at f_lat. */
+int auvi_multi_plan(int64_t n_lat, int n_gpus, int k, int f_lat, int replicate, int64_t* out6);
 int auvi_multi_count(const auvi_multi* m);
 /* Shard k: its device, its single-GPU handle (borrowed) and the lattice rows [row_lo,row_hi) it produces at factor f_lat. */
 int auvi_multi_shard(const auvi_multi* m, int k, int f_lat, int* device, auvi_grid** grid, int64_t* row_lo, int64_t* row_hi);

@@ -116,3 +116,28 @@ def test_gridd_header_matches_reference_layout():
     assert flat == [("double*", "d_grid"), ("int", "num_lon"), ("int", "num_lat"), ("double", "min_lon"),
                     ("double", "max_lon"), ("double", "min_lat"), ("double", "max_lat"), ("double", "lon_step"),
                     ("double", "lat_step"), ("bool", "initialized")]
+
+
+def test_multi_gpu_row_plan_covers_the_lattice_and_its_halo():
+    """auvi_multi_plan (host only): the shards' lattice rows partition the lattice exactly, and every shard holds the grid
+    rows its kernels can touch -- stencil -1/+2 and a radius-10 ring search around a centre that FP64 noise may move by one
+    row (the checks launch_tiled / launch_fill make on the device side: base - 12 .. base + 13)."""
+    import auvi
+    for n_lat in (2, 5, 97, 301, 65536):
+        for n_gpus in (1, 2, 3, 8, 64):
+            for f in (1, 2, 4):
+                total = f * (n_lat - 1) + 1
+                nxt = 0
+                for k in range(n_gpus):
+                    p = auvi.multi_plan(n_lat, n_gpus, k, f)
+                    assert p["row_lo"] == nxt and p["row_hi"] >= p["row_lo"]
+                    nxt = p["row_hi"]
+                    if p["row_hi"] > p["row_lo"]:
+                        need_lo = max(0, p["row_lo"] // f - 12)
+                        need_hi = min(n_lat - 1, (p["row_hi"] - 1) // f + 13)
+                        assert p["in_lo"] <= need_lo and need_hi < p["in_hi"], (n_lat, n_gpus, k, f, p)
+                    r = auvi.multi_plan(n_lat, n_gpus, k, f, replicate=True)
+                    assert (r["in_lo"], r["in_hi"]) == (0, n_lat) and (r["row_lo"], r["row_hi"]) == (p["row_lo"], p["row_hi"])
+                assert nxt == total
+    with pytest.raises(auvi.AuviError):
+        auvi.multi_plan(10, 2, 2)
