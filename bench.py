@@ -22,6 +22,8 @@ One JSON line on rank 0:
               block of the same lattice, all host threads, warmed up; plus the as-shipped single-thread figure
   gather      N > 1, outside `value`: NCCL gather of the row shards to rank 0, and the same gather with no collective --
               the kernel stores into rank 0's buffer through peer memory (auvi_peer_*)
+  same_workload_on_one_gpu  N > 1, rank 0, outside `value`: the whole 65536^2 job on one GPU in the same run (the N = 1 line
+              runs configs[3], a different job: this is the strong-scaling reference of the N > 1 lines)
   single_process_multi_gpu  N > 1, rank 0, outside `value`: the same kind of job through auvi_multi_* (one process
               driving all N GPUs behind the C ABI)
   extra       other BASELINE configs (Mariana 50 % and Grid A through the Point-list API, the reference's own GPU
@@ -723,16 +725,17 @@ def run_fill_sharded(c):
         torch.cuda.synchronize()
 
     gather = gather_to_root(c, g, out, lo, my_rows, n, ms_step)
-    single = None
+    single, one_gpu = None, None
     if not args.no_extra:
         single = single_process_multi_gpu(c)
+        one_gpu = same_workload_on_one_gpu(c)
 
     if rank == 0:
         line = {"metric": METRIC_FILL, "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": fill_config(world),
                 "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-                "methods": methods, "gather": gather, "single_process_multi_gpu": single}
+                "methods": methods, "same_workload_on_one_gpu": one_gpu, "gather": gather, "single_process_multi_gpu": single}
         print(json.dumps(line), flush=True)
     g.close()
 
@@ -810,6 +813,44 @@ def gather_to_root(c, g, out, lo, my_rows, n, ms_step):
         gather["fused_peer_store"] = {"unavailable": repr(exc)[:200]}
     del recv
     return gather
+
+
+def same_workload_on_one_gpu(c):
+    """The strong-scaling reference measured in the same run: the WHOLE 65536^2 grid, same mask, IDW, on rank 0's GPU alone
+    (the other ranks wait on the CPU).  The N = 1 bench line runs BASELINE configs[3], not this workload, so the per-N
+    `value`s of this line and that one are not the same job; this object is what N = 1 of THIS job costs."""
+    torch, auvi = c.torch, c.auvi
+    res = None
+    c.barrier()
+    c.host_barrier()
+    if c.rank == 0:
+        try:
+            n = N_FILL
+            z = synth_grid_device(torch, n, n, 0, n, c.dev)
+            g = auvi.Grid(adopt=dict(ptr=z.data_ptr(), dtype=auvi.F32, n_lat=n, n_lon=n, ld=n, row0=0, rows=n, keep=z),
+                          min_lon=FILL_BOUNDS[0], max_lon=FILL_BOUNDS[1], min_lat=FILL_BOUNDS[2], max_lat=FILL_BOUNDS[3], device=c.dev.index)
+            g.mask_hash(FILL_MASK, seed=42, count=False, stream=c.stream)
+            out = torch.empty((n, n), dtype=torch.float32, device=c.dev)
+            fn = lambda: g.lattice_device(auvi.IDW, auvi.AXIS_NODES, 1, 1, 1, 0, n, out.data_ptr(), n, None, c.stream)
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            res = {"n_gpus": 1, "ms_per_step": ms, "Mcells_per_s": n * n / (ms * 1e-3) / 1e6, "steps": 5,
+                   "what": "the same 65536^2 grid, mask and method on one GPU of this box, in this run"}
+            g.close()
+            del z, out
+            torch.cuda.empty_cache()
+        except Exception as exc:
+            res = {"unavailable": repr(exc)[:200]}
+    c.host_barrier()
+    return res
 
 
 def single_process_multi_gpu(c):
