@@ -129,6 +129,16 @@ struct FillSmem {
 static_assert(sizeof(FillSmem<float>) <= 75 * 1024, "three CTAs per SM need <= 75 KB each (f32 grids)");
 static_assert(sizeof(FillSmem<double>) <= 113 * 1024, "two CTAs per SM (f64 grids)");
 
+// A result's way out.  PATCH = false: a streaming store to the output.  PATCH = true: into the staged tile in shared memory
+// (`dst` then points there) -- a masked cell is never read by a search, candidates are valid cells -- and the finished tile
+// leaves with 16-byte row stores at the end of the kernel: what the output wants when it is PEER memory (the gather fused
+// into the kernel), where per-query 4-byte stores crawl over NVLink.
+template <bool PATCH, typename T>
+__device__ __forceinline__ void put(T* dst, T v) {
+    if (PATCH) *dst = v;
+    else __stcs(dst, v);
+}
+
 template <typename T, int METHOD>
 __device__ __noinline__ T fill_cell_literal(const FillParams<T>* p, int64_t J, int I) {
     return static_cast<T>(interp_exact<T>(p->g, METHOD, __ldg(p->lon.coord + I), __ldg(p->lat.coord + J),
@@ -238,9 +248,9 @@ __device__ __noinline__ T finish_few(int cnt, double v0, double v1, double v2, d
 // so a pass can only come out differently if a remaining value lies above the pass minimum by less than sqrt
 // rounding can close.  That is checked on the sorted chain afterwards; such a query returns false and is replayed
 // with REPLAY = true, which takes the square roots first -- the reference's own comparison, bit for bit.
-template <typename T, int METHOD, int N, bool REPLAY>
+template <typename T, int METHOD, int N, bool REPLAY, bool PATCH>
 __device__ __forceinline__ bool near_query(FillSmem<T>& s, const FillParams<T>& p, uint32_t cand, int q, int k, int c0,
-                                           int r0, int I0, int64_t J0, T* out_tile) {
+                                           int r0, int I0, int64_t J0, T* out_tile, int64_t tile_ld) {
     constexpr int kPasses = METHOD == NN ? 1 : 4;
     const int lj = k / kFW, li = k % kFW;
     const char* const sqx = reinterpret_cast<const char*>(s.sqx + li * (2 * kFSq + 1) + kFSq - 2);   // [dx + 2]
@@ -290,13 +300,14 @@ __device__ __forceinline__ bool near_query(FillSmem<T>& s, const FillParams<T>& 
             d2[e] = dadd(*reinterpret_cast<const double*>(sqx + (off & 0xffffu)), *reinterpret_cast<const double*>(sqy + (off >> 16)));
         } else d2[e] = d[e];
     }
-    __stcs(out_tile + lj * p.out_ld + li, finish_four<T, METHOD>(p, v, d2, pi, pj, I0 + li, J0 + lj));
+    put<PATCH>(out_tile + lj * tile_ld + li, finish_four<T, METHOD>(p, v, d2, pi, pj, I0 + li, J0 + lj));
     return true;
 }
 
-template <typename T, int METHOD, bool FILL>
+template <typename T, int METHOD, bool FILL, bool PATCH = false>
 __global__ void __launch_bounds__(kFThreads, 3)
 fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ FillParams<T> p) {
+    constexpr bool kPatch = PATCH && FILL && METHOD != BILINEAR && METHOD != BILINEAR_SEARCH;   // bilinear READS masked corners
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FillSmem<T>& s = *reinterpret_cast<FillSmem<T>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -307,7 +318,10 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     // 16-byte boundary for TMA (on the node lattice I0 - 12 already is one)
     const int c0 = (I0 / p.f_lon - kFHalo) & ~3;
     const int r0 = static_cast<int>(J0 / p.f_lat) - kFHalo;
-    T* const out_tile = p.out + (J0 - p.row_begin) * p.out_ld + I0;
+    T* const g_out_tile = p.out + (J0 - p.row_begin) * p.out_ld + I0;
+    // where results go: the output, or (PATCH) the tile's own cells inside the staged block
+    T* const out_tile = kPatch ? s.tile + kFHalo * kFBW + kFHalo : g_out_tile;
+    const int64_t tile_ld = kPatch ? kFBW : p.out_ld;
     // two queues live in the general path's list storage until that path starts:
     uint16_t* const queue = reinterpret_cast<uint16_t*>(s.d2);     // masked cells of the tile, compacted (read by phase A1)
     uint16_t* const defer = queue + kFCells;                       // A1 -> A2: queries the 5 x 5 block cannot decide
@@ -410,8 +424,8 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             if (lane == 0 && n_row) base = atomicAdd(&s.qn, n_row);
             base = __shfl_sync(0xffffffffu, base, 0);
             const T* const trow = s.tile + (lj + kFHalo) * kFBW + kFHalo;
-            T* const orow = out_tile + lj * p.out_ld;
-            if (FILL) {
+            T* const orow = g_out_tile + lj * p.out_ld;
+            if (FILL && !kPatch) {
                 if ((v_lo & range_lo) >> lane & 1u) __stcs(orow + lane, trow[lane]);
                 if ((v_hi & range_hi) >> lane & 1u) __stcs(orow + 32 + lane, trow[32 + lane]);
             }
@@ -447,7 +461,7 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             }
             // BILINEAR_SEARCH (opt-in): a query whose four corners are all missing goes on to the ring search
             if (METHOD == BILINEAR_SEARCH && isnan(result) && !isnan(x) && !isnan(y)) defer[atomicAdd(&s.dn, 1)] = static_cast<uint16_t>(k);
-            else __stcs(out_tile + lj * p.out_ld + li, static_cast<T>(result));
+            else put<kPatch>(out_tile + lj * tile_ld + li, static_cast<T>(result));
         }
         if (METHOD == BILINEAR) return;
         __syncthreads();
@@ -464,7 +478,7 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     auto to_literal = [&](int k) {                                  // hand a query to the literal per-query path
         const int slot = atomicAdd(&s.rn, 1);
         if (slot < kFRedoMax) s.redo[slot] = static_cast<uint16_t>(k);
-        else __stcs(out_tile + (k / kFW) * p.out_ld + (k % kFW), fill_cell_literal<T, METHOD>(&p, J0 + k / kFW, I0 + k % kFW));
+        else put<kPatch>(out_tile + (k / kFW) * tile_ld + (k % kFW), fill_cell_literal<T, METHOD>(&p, J0 + k / kFW, I0 + k % kFW));
     };
 
     // ---- phase A1: the 5 x 5 block around each query's centre decides most searches ---------------------------
@@ -481,7 +495,7 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         int near_bin = -1;
         if (!live) {
         } else if (isnan(s.x[li]) || isnan(s.y[lj])) {
-            __stcs(out_tile + lj * p.out_ld + li, static_cast<T>(qnan()));   // query out of bounds
+            put<kPatch>(out_tile + lj * tile_ld + li, static_cast<T>(qnan()));   // query out of bounds
         } else {
             const int ci = s.cx[li] - c0, cj = s.cy[lj] - r0;       // search centre in tile coordinates
             if ((ci < 11) | (ci > kFBW - 12) | (cj < 11) | (cj > kFBH - 12)) to_literal(k);   // never for node queries
@@ -734,7 +748,7 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 d2v[e] = ld2[e * kFThreads];
                 pi[e] = cig + dx; pj[e] = cjg + dy;
             }
-            __stcs(out_tile + lj * p.out_ld + li, finish_four<T, METHOD>(p, v, d2v, pi, pj, I0 + li, J0 + lj));
+            put<kPatch>(out_tile + lj * tile_ld + li, finish_four<T, METHOD>(p, v, d2v, pi, pj, I0 + li, J0 + lj));
         } else {                                                    // the search ran out of rings (GridH.cpp:291-298)
             double fv[3], fd[3];
 #pragma unroll
@@ -743,7 +757,7 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 fv[e] = static_cast<double>(s.tile[(cj + (code >> 5) - 10) * kFBW + ci + (code & 31) - 10]);
                 fd[e] = e < cnt ? ld2[e * kFThreads] : 0.0;
             }
-            __stcs(out_tile + lj * p.out_ld + li, finish_few<T, METHOD>(cnt, fv[0], fv[1], fv[2], fd[0], fd[1], fd[2]));
+            put<kPatch>(out_tile + lj * tile_ld + li, finish_few<T, METHOD>(cnt, fv[0], fv[1], fv[2], fd[0], fd[1], fd[2]));
         }
     };
 
@@ -771,9 +785,9 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             if (active) {
                 const int k = s.reck[q];
                 bool ok;
-                if (nmax <= 4) ok = near_query<T, METHOD, 4, false>(s, p, cand, q, k, c0, r0, I0, J0, out_tile);
-                else if (nmax <= 6) ok = near_query<T, METHOD, 6, false>(s, p, cand, q, k, c0, r0, I0, J0, out_tile);
-                else ok = near_query<T, METHOD, kFNear, false>(s, p, cand, q, k, c0, r0, I0, J0, out_tile);
+                if (nmax <= 4) ok = near_query<T, METHOD, 4, false, kPatch>(s, p, cand, q, k, c0, r0, I0, J0, out_tile, tile_ld);
+                else if (nmax <= 6) ok = near_query<T, METHOD, 6, false, kPatch>(s, p, cand, q, k, c0, r0, I0, J0, out_tile, tile_ld);
+                else ok = near_query<T, METHOD, kFNear, false, kPatch>(s, p, cand, q, k, c0, r0, I0, J0, out_tile, tile_ld);
                 if (!ok) {
                     const int slot = atomicAdd(&s.tn, 1);
                     if (slot < kFReplayMax) s.replay[slot] = static_cast<uint16_t>(q);
@@ -788,7 +802,7 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     const int tn = min(s.tn, kFReplayMax);
     for (int t = tid; t < tn; t += kFThreads) {
         const int q = s.replay[t];
-        near_query<T, METHOD, kFNear, true>(s, p, s.rec[q] & kC4, q, s.reck[q], c0, r0, I0, J0, out_tile);
+        near_query<T, METHOD, kFNear, true, kPatch>(s, p, s.rec[q] & kC4, q, s.reck[q], c0, r0, I0, J0, out_tile, tile_ld);
     }
     __syncthreads();
     // ---- kriging of the near-path picks: full warps, nothing else live ------------------------------------------------
@@ -810,7 +824,7 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 pk.v[e] = static_cast<double>(centre[s.cell_tile[c]]);
                 pk.d[e] = 0.0;
             }
-            __stcs(out_tile + lj * p.out_ld + li,
+            put<kPatch>(out_tile + lj * tile_ld + li,
                    static_cast<T>(kriging_from_picked(p.g, pk, __ldg(p.lon.coord + I0 + li), __ldg(p.lat.coord + J0 + lj))));
         }
     }
@@ -818,7 +832,32 @@ fill_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     const int rn = min(s.rn, kFRedoMax);
     for (int q = tid; q < rn; q += kFThreads) {
         const int k = s.redo[q];
-        __stcs(out_tile + (k / kFW) * p.out_ld + (k % kFW), fill_cell_literal<T, METHOD>(&p, J0 + k / kFW, I0 + k % kFW));
+        put<kPatch>(out_tile + (k / kFW) * tile_ld + (k % kFW), fill_cell_literal<T, METHOD>(&p, J0 + k / kFW, I0 + k % kFW));
+    }
+    // ---- PATCH: the finished tile leaves -- pass-through cells and patched results in one sweep of 16-byte row stores ------
+    if (kPatch) {
+        __syncthreads();
+        constexpr int VEC = 16 / static_cast<int>(sizeof(T)), VPR = kFW / VEC;
+        const int nrows = static_cast<int>(min(static_cast<int64_t>(kFH), p.row_end - J0));
+        const int ncols = min(kFW, p.n_out_cols - I0);
+        if (p.vec_ok) {
+            for (int k = tid; k < nrows * VPR; k += kFThreads) {
+                const int lj = k / VPR, col = (k - lj * VPR) * VEC;
+                const T* const src = out_tile + lj * kFBW + col;
+                T* const dst = g_out_tile + lj * p.out_ld + col;
+                if (col + VEC <= ncols) {
+                    if constexpr (sizeof(T) == 4) __stcs(reinterpret_cast<float4*>(dst), *reinterpret_cast<const float4*>(src));
+                    else __stcs(reinterpret_cast<double2*>(dst), *reinterpret_cast<const double2*>(src));
+                } else {
+                    for (int c = 0; col + c < ncols; ++c) __stcs(dst + c, src[c]);
+                }
+            }
+        } else {
+            for (int k = tid; k < nrows * kFW; k += kFThreads) {
+                const int lj = k / kFW, li = k - lj * kFW;
+                if (li < ncols) __stcs(g_out_tile + lj * p.out_ld + li, out_tile[lj * kFBW + li]);
+            }
+        }
     }
 }
 
@@ -1015,12 +1054,27 @@ static cudaError_t launch_fill_t(const GridDesc& d, const AxisTables& lat, const
         p.n_out_cols = lon.n;
         p.f_lat = d.n_lat > 1 ? (lat.n - 1) / (d.n_lat - 1) : 1;
         p.f_lon = d.n_lon > 1 ? (lon.n - 1) / (d.n_lon - 1) : 1;
-        p.tiles_x = 0; p.n_tiles = 0; p.vec_ok = 0;
+        p.tiles_x = 0; p.n_tiles = 0;
+        p.vec_ok = (reinterpret_cast<uintptr_t>(out) % 16 == 0 && (out_ld * sizeof(T)) % 16 == 0) ? 1 : 0;
         if (p.f_lat < 1 || p.f_lon < 1 || (FILL && (p.f_lat != 1 || p.f_lon != 1))) return cudaErrorInvalidValue;
         CUtensorMap tmap;
         memset(&tmap, 0, sizeof tmap);
         p.use_tma = make_grid_tensor_map(d, kFBW, kFBH, &tmap, /*nan_fill=*/true) ? 1 : 0;
         auto kern = fill_tiled_kernel<T, METHOD, FILL>;
+        if constexpr (FILL && METHOD != BILINEAR_SEARCH) {
+            // results patched into the staged tile + 16-byte row stores when the output is PEER memory (the gather fused into
+            // the kernel): 8 % slower than per-query stores into local HBM, several times faster over NVLink
+            static const int force = [] { const char* e = getenv("AUVI_FILL_PATCH"); return e ? atoi(e) : -1; }();
+            bool patch = force > 0;
+            if (force < 0) {
+                cudaPointerAttributes attr;
+                int dev = 0;
+                if (cudaGetDevice(&dev) == cudaSuccess && cudaPointerGetAttributes(&attr, out) == cudaSuccess)
+                    patch = attr.type == cudaMemoryTypeDevice && attr.device != dev;
+                else cudaGetLastError();
+            }
+            if (patch) kern = fill_tiled_kernel<T, METHOD, FILL, true>;
+        }
         const size_t smem = sizeof(FillSmem<T>);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;

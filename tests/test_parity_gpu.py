@@ -722,3 +722,44 @@ def test_adopted_grid_with_unaligned_pitch_takes_the_plain_load_path(auvi, torch
             assert float((u[ok].double() - v[ok].double()).abs().max()) <= 1e-3 + 1e-5 * 4000
         assert bool((u[:, cols:] == 7.0).all())                     # the padding of the output rows is untouched
     g.close()
+
+
+def test_fill_patched_tile_variant_equals_the_default():
+    """fill_tiled_kernel has a second way out for its results: patched into the staged tile and stored as whole 16-byte rows
+    (picked automatically when the output is peer memory: the gather fused into the kernel).  AUVI_FILL_PATCH=1 forces it
+    (read once per process, hence the child): every method, both dtypes, aligned and unaligned output pitches, must produce
+    the bits of the default variant's output -- recorded here by a first child without the variable."""
+    import hashlib
+    import subprocess
+    code = r'''
+import sys, hashlib, numpy as np, torch
+sys.path.insert(0, "auv-real-time-interpolation_b200/python"); sys.path.insert(0, ".")
+import auvi
+for dt, tdt in ((auvi.F32, torch.float32), (auvi.F64, torch.float64)):
+    n_lat, n_lon = 517, 1301
+    jj = torch.arange(n_lat, device="cuda", dtype=torch.float64)[:, None]; ii = torch.arange(n_lon, device="cuda", dtype=torch.float64)[None, :]
+    z = (-4000.0 + 900.0 * torch.sin(ii * 0.013) * torch.cos(jj * 0.017) + 0.37 * ii - 0.21 * jj).to(tdt).contiguous()
+    g = auvi.Grid(adopt=dict(ptr=z.data_ptr(), dtype=dt, n_lat=n_lat, n_lon=n_lon, ld=n_lon, row0=0, rows=n_lat, keep=z), min_lon=-30.9967, max_lon=-29.4993, min_lat=-0.5035, max_lat=1.0071)
+    for frac in (0.3, 0.7, 0.95):
+        z2 = z.clone(); g2 = auvi.Grid(adopt=dict(ptr=z2.data_ptr(), dtype=dt, n_lat=n_lat, n_lon=n_lon, ld=n_lon, row0=0, rows=n_lat, keep=z2), min_lon=-30.9967, max_lon=-29.4993, min_lat=-0.5035, max_lat=1.0071)
+        g2.mask_hash(frac, seed=5, count=False)
+        for ld in (n_lon, n_lon + 3):
+            for meth in (auvi.NN, auvi.CUBIC, auvi.IDW, auvi.KRIGING, auvi.BILINEAR):
+                out = torch.full((n_lat, ld), 7.0, dtype=tdt, device="cuda")
+                g2.lattice_device(meth, auvi.AXIS_NODES, 1, 1, 1, 0, n_lat, out.data_ptr(), ld, None, torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+                assert bool((out[:, n_lon:] == 7.0).all())
+                print(dt, frac, ld, meth, hashlib.sha1(out.cpu().numpy().tobytes()).hexdigest())
+        g2.close()
+    g.close()
+'''
+    outs = []
+    for patch in (None, "1"):
+        env = dict(os.environ)
+        env.pop("AUVI_FILL_PATCH", None)
+        if patch:
+            env["AUVI_FILL_PATCH"] = patch
+        r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+        outs.append(r.stdout)
+    assert len(outs[0].splitlines()) == 2 * 3 * 2 * 5 and outs[0] == outs[1]
