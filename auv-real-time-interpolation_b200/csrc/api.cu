@@ -759,6 +759,22 @@ int auvi_lattice(auvi_grid* g, int method, int axis_kind, int f_lat, int f_lon, 
 namespace {
 std::mutex g_peer_mu;
 std::map<void*, void*> g_peer_base;                   // pointer handed out by auvi_peer_open -> base of the IPC mapping
+std::map<uintptr_t, size_t> g_peer_range;             // base of an IPC mapping -> its size
+}
+
+bool auvi::output_is_peer_memory(const void* p) {
+    {
+        std::lock_guard<std::mutex> lk(g_peer_mu);
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        auto it = g_peer_range.upper_bound(a);
+        if (it != g_peer_range.begin()) { --it; if (a < it->first + it->second) return true; }
+    }
+    cudaPointerAttributes attr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaPointerGetAttributes(&attr, p) == cudaSuccess)
+        return attr.type == cudaMemoryTypeDevice && attr.device != dev;      // a peer device of this process
+    cudaGetLastError();
+    return false;
 }
 
 int auvi_peer_export(const void* dev_ptr, unsigned char* handle72) {
@@ -793,8 +809,19 @@ int auvi_peer_open(const unsigned char* handle72, void** out_ptr) {
     void* base = nullptr;
     AUVI_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
     *out_ptr = static_cast<char*>(base) + off;
+    size_t size = 0;
+    {   // the extent of the mapping, so that kernels can tell that an output pointer is peer memory
+        typedef CUresult (*range_fn)(CUdeviceptr*, size_t*, CUdeviceptr);
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CUdeviceptr b = 0;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &sym, cudaEnableDefault, &q) == cudaSuccess && sym &&
+            reinterpret_cast<range_fn>(sym)(&b, &size, reinterpret_cast<CUdeviceptr>(base)) != CUDA_SUCCESS) size = 0;
+        else cudaGetLastError();
+    }
     std::lock_guard<std::mutex> lk(g_peer_mu);
     g_peer_base[*out_ptr] = base;
+    if (size) g_peer_range[reinterpret_cast<uintptr_t>(base)] = size;
     return 0;
 }
 
@@ -807,6 +834,7 @@ int auvi_peer_close(void* ptr) {
         if (it == g_peer_base.end()) return fail("not a pointer from auvi_peer_open");
         base = it->second;
         g_peer_base.erase(it);
+        g_peer_range.erase(reinterpret_cast<uintptr_t>(base));
     }
     AUVI_CUDA(cudaIpcCloseMemHandle(base));
     return 0;

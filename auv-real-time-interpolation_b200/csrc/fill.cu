@@ -1062,17 +1062,12 @@ static cudaError_t launch_fill_t(const GridDesc& d, const AxisTables& lat, const
         p.use_tma = make_grid_tensor_map(d, kFBW, kFBH, &tmap, /*nan_fill=*/true) ? 1 : 0;
         auto kern = fill_tiled_kernel<T, METHOD, FILL>;
         if constexpr (FILL && METHOD != BILINEAR_SEARCH) {
-            // results patched into the staged tile + 16-byte row stores when the output is PEER memory (the gather fused into
-            // the kernel): 8 % slower than per-query stores into local HBM, several times faster over NVLink
+            // Results patched into the staged tile + 16-byte row stores, or one streaming store per query?  Into local HBM the
+            // two are within 1 % for IDW and the 4-nearest mean, row stores win 2-4 % for kriging and lose 3.5 % for NN
+            // (profiles/r02_fill_patch_ab.txt).  Into PEER memory (the gather fused into the kernel)
+            // per-query 4-byte stores crawl over NVLink: row stores for every method.  AUVI_FILL_PATCH=0/1 forces (A/B, tests).
             static const int force = [] { const char* e = getenv("AUVI_FILL_PATCH"); return e ? atoi(e) : -1; }();
-            bool patch = force > 0;
-            if (force < 0) {
-                cudaPointerAttributes attr;
-                int dev = 0;
-                if (cudaGetDevice(&dev) == cudaSuccess && cudaPointerGetAttributes(&attr, out) == cudaSuccess)
-                    patch = attr.type == cudaMemoryTypeDevice && attr.device != dev;
-                else cudaGetLastError();
-            }
+            const bool patch = force >= 0 ? force != 0 : (METHOD != NN || output_is_peer_memory(out));
             if (patch) kern = fill_tiled_kernel<T, METHOD, FILL, true>;
         }
         const size_t smem = sizeof(FillSmem<T>);

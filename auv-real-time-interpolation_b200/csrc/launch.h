@@ -101,6 +101,10 @@ cudaError_t launch_csv_parse(const char* text, const int64_t* pos, int64_t n_fie
 cudaError_t launch_csv_patch(void* out, int64_t ld, int n_cols, int dtype, const int64_t* idx, const double* val, int64_t n,
                              cudaStream_t st);
 
+// api.cu: does `p` lie in memory of ANOTHER device -- mapped by auvi_peer_open (CUDA IPC) or allocated on a peer device of this
+// process?  The gap-fill kernel then leaves its tiles as 16-byte row stores instead of per-query stores.
+bool output_is_peer_memory(const void* p);
+
 // Encodes a 2-D tiled tensor map over the grid slab; returns false when TMA cannot address it.  nan_fill: box elements
 // outside the slab arrive as NaN instead of zero (the gap-fill kernels treat "outside" and "masked" alike).
 bool make_grid_tensor_map(const GridDesc& d, int box_w, int box_h, CUtensorMap* out, bool nan_fill = false);
