@@ -762,7 +762,7 @@ std::map<void*, void*> g_peer_base;                   // pointer handed out by a
 std::map<uintptr_t, size_t> g_peer_range;             // base of an IPC mapping -> its size
 }
 
-bool auvi::output_is_peer_memory(const void* p) {
+extern "C++" bool auvi::output_is_peer_memory(const void* p) {
     {
         std::lock_guard<std::mutex> lk(g_peer_mu);
         const uintptr_t a = reinterpret_cast<uintptr_t>(p);
