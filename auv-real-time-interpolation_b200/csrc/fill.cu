@@ -29,6 +29,9 @@
 //      literal per-query path (exact.cuh).
 //   7. Epilogue on the four picks: mean / first pick / FP32 IDW weights through the SFU reciprocal / kriging (its FP64
 //      solve runs as a phase of its own over the recorded picks).
+//   8. PATCH instantiations (kriging, IDW, 4-nearest mean by default; every method when the output is peer memory): results are
+//      patched into the staged tile -- a masked cell is never read by a search, candidates are valid cells -- and the finished
+//      tile leaves as 16-byte row stores; otherwise one streaming store per query and early pass-through stores.
 //
 // Algorithmic HBM bytes: sizeof(T) read + sizeof(T) written per cell; the kernel is issue-bound (integer /
 // bit work + FP64 distance compares), not HBM-bound.
