@@ -24,9 +24,19 @@ cases.append(("grid_a_5M_random_points", za, BOUNDS, pa))
 mc = ob.masked_case("mariana", 0.5)
 cases.append(("mariana_50pct", mc["z"], mc["bounds"], mc["pts"]))
 stream = torch.cuda.current_stream().cuda_stream
+# our GridD CLASS (host/GridD.cpp over libauvi) behind the same kind of C shim as the reference's: vector<Point> in and out
+import ctypes as C
+_dp = C.POINTER(C.c_double)
+ours = C.CDLL(os.path.join(ROOT, "auv-real-time-interpolation_b200", "lib", "libgridd_c.so"))
+ours.ourd_create.argtypes = [_dp, C.c_int, C.c_int] + [C.c_double] * 4; ours.ourd_create.restype = C.c_void_p
+ours.ourd_destroy.argtypes = [C.c_void_p]
+ours.ourd_batch.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int64, _dp]; ours.ourd_batch.restype = C.c_double
 for tag, z, bounds, pts in cases:
     ref = ob.ReferenceGPU(z, *bounds)
     g = auvi.Grid(z, *bounds, device=local)
+    zc = np.ascontiguousarray(z, dtype=np.float64)
+    og = ours.ourd_create(zc.ctypes.data_as(_dp), zc.shape[0], zc.shape[1], *bounds)
+    o_cls = np.empty(pts.shape[0])
     d_pts = torch.from_numpy(pts).cuda()
     d_out = torch.empty(pts.shape[0], dtype=torch.float64, device="cuda")
     tab = {}
@@ -49,14 +59,18 @@ for tag, z, bounds, pts in cases:
         for _ in range(5): fn()
         e1.record(); torch.cuda.synchronize()
         ok_ms = e0.elapsed_time(e1) / 5
+        ours.ourd_batch(og, meth, pts.ctypes.data_as(_dp), pts.shape[0], o_cls.ctypes.data_as(_dp))
+        c_ms = float(np.mean([ours.ourd_batch(og, meth, pts.ctypes.data_as(_dp), pts.shape[0], o_cls.ctypes.data_as(_dp)) for _ in range(3)]))
+        assert np.array_equal(np.nan_to_num(o_cls, nan=7.0), np.nan_to_num(o_out, nan=7.0))
         fin = ~np.isnan(r_out)
         tab[name] = {"reference_gpu_kernel_ms": k_ms, "ours_kernel_ms": ok_ms, "kernel_speedup": k_ms / ok_ms,
                      "reference_gpu_e2e_ms": float(np.mean(r_ms)), "ours_e2e_ms": o_ms, "e2e_speedup": float(np.mean(r_ms)) / o_ms,
+                     "ours_gridd_class_e2e_ms": c_ms, "gridd_class_e2e_speedup": float(np.mean(r_ms)) / c_ms,
                      "same_nan_mask": bool(np.array_equal(np.isnan(r_out), np.isnan(o_out))),
                      "kernel_equals_batch": bool(np.array_equal(np.nan_to_num(k_out, nan=7.0), np.nan_to_num(r_out, nan=7.0))),
                      "max_abs_diff_m": float(np.max(np.abs(r_out[fin] - o_out[fin]))) if fin.any() else 0.0, "n": int(pts.shape[0])}
     out[tag] = tab
-    g.close(); ref.close()
+    g.close(); ref.close(); ours.ourd_destroy(og)
     del d_pts, d_out
 sys.stdout.flush()
 print("\n" + json.dumps(out))
