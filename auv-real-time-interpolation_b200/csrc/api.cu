@@ -427,6 +427,19 @@ int pack_threads(int64_t cnt) {
 
 extern "C" {
 
+// First-touch a fresh host allocation from the library's worker threads (one write per 4 KiB page): a caller that must
+// return a newly allocated 100 MB std::vector -- GridD::batch*, whose signature returns the result vector by value -- pays
+// ~40 ms of single-threaded page faults for it otherwise (profiles/r02_points_vs_reference_gpu.txt).
+int auvi_host_prefault(void* p, int64_t bytes) {
+    if (!p || bytes <= 0) return 0;
+    HostPool& pool = HostPool::get();
+    char* const base = static_cast<char*>(p);
+    pool.for_range(bytes, bytes < (8 << 20) ? 1 : pool.size(), 4096, [&](int64_t lo, int64_t hi) {
+        for (int64_t at = lo; at < hi; at += 4096) base[at] = 0;
+    });
+    return 0;
+}
+
 int auvi_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

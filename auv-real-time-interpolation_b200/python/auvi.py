@@ -71,6 +71,7 @@ SYMBOLS = {
     "auvi_multi_sync": (_i32, [_vp]),
     "auvi_multi_last_kernel_ms": (C.c_float, [_vp]),
     "auvi_multi_interp_points": (_i32, [_vp, _i32, _vp, _i64, _i64, _vp, _i64]),
+    "auvi_host_prefault": (_i32, [_vp, _i64]),
     "auvi_last_error": (C.c_char_p, []),
     "auvi_last_kernel_ms": (C.c_float, [_vp]),
     "auvi_launch_count": (_i64, []),

@@ -226,6 +226,11 @@ float auvi_multi_last_kernel_ms(const auvi_multi* m);        /* device time of t
 int auvi_multi_interp_points(auvi_multi* m, int method, const void* host_pts, int64_t n, int64_t stride_bytes, void* host_out,
                              int64_t out_stride_bytes);
 
+/* Host only: first-touch `bytes` of freshly allocated host memory at `p` from the library's worker threads (GridD::batch*
+ * must return a new std::vector<Point> by value -- include/GridD.h:69-85 --: a 120 MB result vector costs ~40 ms of
+ * single-threaded page faults otherwise).  Writes one zero byte per 4 KiB page: only for memory whose contents do not matter yet. */
+int auvi_host_prefault(void* p, int64_t bytes);
+
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 const char* auvi_last_error(void);          /* thread-local message of the last failure */
 float auvi_last_kernel_ms(const auvi_grid* g); /* device time of the kernels of the last synchronous call */
