@@ -434,7 +434,7 @@ int auvi_host_prefault(void* p, int64_t bytes) {
     if (!p || bytes <= 0) return 0;
     HostPool& pool = HostPool::get();
     char* const base = static_cast<char*>(p);
-    pool.for_range(bytes, bytes < (8 << 20) ? 1 : pool.size(), 4096, [&](int64_t lo, int64_t hi) {
+    pool.for_range(bytes, bytes < (2 << 20) ? 1 : pool.size(), 4096, [&](int64_t lo, int64_t hi) {
         for (int64_t at = lo; at < hi; at += 4096) base[at] = 0;
     });
     return 0;
