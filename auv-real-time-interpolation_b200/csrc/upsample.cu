@@ -110,7 +110,7 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     T* tile = reinterpret_cast<T*>(smem_raw);                      // [bh][bw]
     __shared__ uint64_t bar;
     __shared__ int s_top[kTileRowsMax];                            // local row of the first tap
-    __shared__ double s_ty[kF64 ? kTileRowsMax : 1];               // frac(pos_y), NaN if out of bounds
+    __shared__ double2 s_ty[kF64 ? kTileRowsMax : 1];              // frac(pos_y) (NaN if out of bounds) and half of it
     __shared__ float4 s_wy[kF64 ? 1 : kTileRowsMax];               // FP32 vertical tap weights
 
     const int tid = threadIdx.x;
@@ -161,7 +161,7 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
         const double ty = dsub(py, static_cast<double>(by));       // NaN stays NaN
         s_top[tid] = by - LO - r0;
         if constexpr (kF64) {
-            s_ty[tid] = ty;
+            s_ty[tid] = make_double2(ty, dmul(0.5, ty));
         } else {
             float4 w;
             if (kCubic) cr_weights(static_cast<float>(ty), w.x, w.y, w.z, w.w);
@@ -176,6 +176,7 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     const T* const my_tile = tile + my_slab * box_stride;
     int ox[COLS];
     double txd[COLS];
+    double thx[kF64 && kCubic ? COLS : 1];                         // txd / 2: the last factor of each Catmull-Rom product (exact.cuh)
     float wx[kF64 ? 1 : COLS][4];
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
@@ -185,6 +186,7 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
         if (I < W) { px = __ldg(p.lon.pos + I); bx = __ldg(p.lon.base + I); }
         txd[c] = dsub(px, static_cast<double>(bx));
         ox[c] = bx - LO - c0;
+        if constexpr (kF64 && kCubic) thx[c] = dmul(0.5, txd[c]);
         if constexpr (!kF64) {
             if (kCubic) cr_weights(static_cast<float>(txd[c]), wx[c][0], wx[c][1], wx[c][2], wx[c][3]);
             else { wx[c][0] = 1.f - static_cast<float>(txd[c]); wx[c][1] = static_cast<float>(txd[c]); wx[c][2] = 0.f; wx[c][3] = 0.f; }
@@ -225,19 +227,23 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     // ---- horizontal pass of one tile row for this thread's columns --------------------------------
     // A NaN anywhere in a footprint (or a NaN weight: out of bounds) surfaces in the horizontal pass
     // of some row the output uses, so it is enough to probe those (cheaper than probing every output).
+    // FP32: the probe is a running sum (one FADD).  FP64: the kernel is bound by the FP64 pipe, so the probe is integer work on
+    // the OUTPUTS instead -- every window row feeds some output of this thread, a NaN tap / weight therefore reaches one -- as the
+    // running maximum of |v|'s high word (non-finite: >= 0x7ff00000).
     T probe = 0;
+    int probe_hi = 0;
     auto hrow = [&](const T* r, T (&dst)[COLS]) {
 #pragma unroll
         for (int c = 0; c < COLS; ++c) {
             const T* q = r + ox[c];
             if constexpr (kF64) {
-                if constexpr (kCubic) dst[c] = catmull_rom_exact(q[0], q[1], q[2], q[3], txd[c]);
+                if constexpr (kCubic) dst[c] = catmull_rom_exact_h(q[0], q[1], q[2], q[3], txd[c], thx[c]);
                 else dst[c] = dadd(dmul(dsub(1.0, txd[c]), q[0]), dmul(txd[c], q[1]));
             } else {
                 if constexpr (kCubic) dst[c] = fmaf(wx[c][3], q[3], fmaf(wx[c][2], q[2], fmaf(wx[c][1], q[1], wx[c][0] * q[0])));
                 else dst[c] = fmaf(wx[c][1], q[1], wx[c][0] * q[0]);
             }
-            probe += dst[c];
+            if constexpr (!kF64) probe += dst[c];
         }
     };
     // one output row from the window; `ph` = slot holding the window's first row (a constant once the
@@ -245,13 +251,14 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     auto emit = [&](int jr, const T (&h)[TAPS][COLS], int ph) {
         T v[COLS];
         if constexpr (kF64) {
-            const double ty = s_ty[jr];
-            probe += ty;
+            const double2 ty2 = s_ty[jr];
+            const double ty = ty2.x;
 #pragma unroll
             for (int c = 0; c < COLS; ++c) {
                 if constexpr (kCubic)
-                    v[c] = catmull_rom_exact(h[ph % TAPS][c], h[(ph + 1) % TAPS][c], h[(ph + 2) % TAPS][c], h[(ph + 3) % TAPS][c], ty);
+                    v[c] = catmull_rom_exact_h(h[ph % TAPS][c], h[(ph + 1) % TAPS][c], h[(ph + 2) % TAPS][c], h[(ph + 3) % TAPS][c], ty, ty2.y);
                 else v[c] = dadd(dmul(dsub(1.0, ty), h[ph % TAPS][c]), dmul(ty, h[(ph + 1) % TAPS][c]));
+                probe_hi = max(probe_hi, __double2hiint(v[c]) & 0x7fffffff);
             }
         } else {
             const float4 w = s_wy[jr];
@@ -295,7 +302,7 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
         }
     }
 swept:
-    const bool dirty = isnan(probe);
+    const bool dirty = kF64 ? probe_hi >= 0x7ff00000 : isnan(probe);
     if (!dirty) return;
     // ---- second sweep, only for threads that produced a NaN: re-read the cells this thread wrote
     // and replace every NaN by the exact per-query evaluation (ring-search fallbacks, NaN-corner
