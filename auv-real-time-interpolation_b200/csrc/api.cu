@@ -55,9 +55,11 @@ struct AxisOwned {
     double* d_coord = nullptr;
     double* d_pos = nullptr;
     int* d_base = nullptr;
+    mutable int window_mode = -1;                                  // upsample.cu: verdict of the window-load pattern check, cached
     AxisTables view() const {
         AxisTables t;
         t.coord = d_coord; t.pos = d_pos; t.base = d_base; t.h_base = base.data();
+        t.window_mode_cache = &window_mode;
         t.n = static_cast<int>(coord.size());
         return t;
     }
@@ -172,7 +174,7 @@ struct auvi_grid {
     size_t d_rows_bytes = 0;
     std::map<long long, AxisOwned*> axes;             // key: which*2^40 + kind*2^32 + factor
     float last_ms = 0.f;
-    int last_tma = 0;
+    int last_tma = 0, last_window = 0;
     // opt-in AUVI_KRIGING_FITTED: exponential model c0 + c1 * (1 - exp(-h / range)) fitted to this grid (or set by the caller)
     bool vg_valid = false;
     double vg_c0 = 0.0, vg_c1 = 0.0, vg_range = 0.0;
@@ -467,6 +469,7 @@ const char* auvi_last_error(void) { return t_error.c_str(); }
 int64_t auvi_launch_count(void) { return g_launches.load(); }
 float auvi_last_kernel_ms(const auvi_grid* g) { return g ? g->last_ms : 0.f; }
 int auvi_uses_tma(const auvi_grid* g) { return g ? g->last_tma : 0; }
+int auvi_uses_window(const auvi_grid* g) { return g ? g->last_window : 0; }
 
 int auvi_grid_create_slab(const void* host_rows, int dtype, int64_t n_lat, int64_t n_lon, int64_t row0, int64_t rows,
                           double min_lon, double max_lon, double min_lat, double max_lat, int device, auvi_grid** out) {
@@ -682,6 +685,7 @@ int auvi_lattice_device(auvi_grid* g, int method, int axis_kind, int f_lat, int 
     if (e != cudaSuccess) return fail_cuda("lattice launch", e);
     g_launches.fetch_add(info.launches);
     g->last_tma = info.used_tma;
+    g->last_window = info.used_window;
     return 0;
 }
 

@@ -123,6 +123,22 @@ __device__ __forceinline__ double catmull_rom_exact_h(double p0, double p1, doub
     const double cub = dmul(dmul(dmul(cc, t), t), th);
     return dadd(dadd(dadd(p1, lin), quad), cub);
 }
+// The same evaluation in two steps: the three coefficients depend on the taps only, so a caller that evaluates several t on one
+// set of taps (the tiled upsample: f_lat output rows under one window of four input rows) forms them once.
+struct CatmullCoef { double a, qc, cc; };
+__device__ __forceinline__ CatmullCoef catmull_rom_coef(double p0, double p1, double p2, double p3) {
+    CatmullCoef k;
+    k.a = dadd(-p0, p2);
+    k.qc = dsub(__fma_rn(4.0, p2, __fma_rn(2.0, p0, -dmul(5.0, p1))), p3);
+    k.cc = dadd(dsub(dadd(-p0, dmul(3.0, p1)), dmul(3.0, p2)), p3);
+    return k;
+}
+__device__ __forceinline__ double catmull_rom_eval(const CatmullCoef& k, double p1, double t, double th) {
+    const double lin = dmul(k.a, th);
+    const double quad = dmul(dmul(k.qc, t), th);
+    const double cub = dmul(dmul(dmul(k.cc, t), t), th);
+    return dadd(dadd(dadd(p1, lin), quad), cub);
+}
 __device__ __forceinline__ double catmull_rom_exact(double p0, double p1, double p2, double p3, double t) {
     return catmull_rom_exact_h(p0, p1, p2, p3, t, dmul(0.5, t));
 }

@@ -46,6 +46,7 @@ struct AxisTables {
     const int* base = nullptr;     // device: floor(pos); for out-of-bounds entries the nearest valid one
     const int* h_base = nullptr;   // host copy of base (tile sizing)
     int n = 0;                     // number of output indices
+    int* window_mode_cache = nullptr;  // host, optional: -1 = not yet checked, else upsample.cu's window_mode() verdict for this axis
 };
 
 // points.cu
@@ -56,6 +57,7 @@ cudaError_t launch_points(const GridDesc& d, int method, const double* pts, int6
 struct LaunchInfo {
     int launches = 0;              // kernels launched
     int used_tma = 0;              // 1 if the input tiles were staged by TMA
+    int used_window = 0;           // window-load form of the FP32 bicubic kernel: 0 generic, 1 / 2 = longitude factor
 };
 
 // upsample.cu -- lattice mode: out[(J-row_begin)*out_ld + I] for J in [row_begin,row_end), all I.

@@ -96,10 +96,23 @@ __device__ __noinline__ T lattice_cell_exact(const TileParams<T>* p, int64_t J, 
 // columns (one 16-byte vector store per output row); a row group sweeps its half of the tile's rows
 // top to bottom, keeping the horizontal pass of the TAPS input rows under the current output row in
 // registers and sliding that window as the (group-uniform) latitude table advances.
-template <typename T, int METHOD>
+//
+// WIN (FP32 bicubic at longitude factors 1 and 2 only; 0 = off): with a thread owning four adjacent output columns, adjacent
+// lanes read their taps 4 / f_lon words apart -- 4-way (f_lon = 1) and 2-way (f_lon = 2) bank conflicts on sixteen 4-byte
+// shared-memory loads per tile row, which made these launches LSU-bound (0.80-0.88 of the HBM peak,
+// profiles/r02_ncu_upsample_small_factor.txt).  Here the thread loads the WINDOW that holds all its taps with three vector
+// loads -- eight words from an 8-byte aligned start at f_lon = 1 (LDS.64, LDS.128, LDS.64), six at f_lon = 2 (3 x LDS.64) --
+// and column c applies five weights to window words s_c .. s_c + 4 (s_c = c, resp. c / 2): its four Catmull-Rom weights
+// shifted by k_c in {0, 1}, the fifth zero.  k_c absorbs the FP64 noise that moves floor() of a node-aligned query one cell
+// down.  The host verifies on the longitude table that every column fits this pattern
+// (window_mode) and launches the generic form otherwise.  A zero weight on a NaN tap yields NaN: such an output goes to the
+// exact re-evaluation like any other dirty one.
+template <typename T, int METHOD, int WIN = 0>
 __global__ void __launch_bounds__(kTileThreads, sizeof(T) == 4 ? 4 : 3)
 upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileParams<T> p) {
     constexpr bool kCubic = (METHOD == CUBIC);
+    static_assert(WIN == 0 || (METHOD == CUBIC && sizeof(T) == 4), "window loads: FP32 bicubic only");
+    constexpr int WN = WIN == 1 ? 8 : 6;                           // window words
     constexpr int LO = kCubic ? 1 : 0;            // taps start at base-LO
     constexpr int TAPS = kCubic ? 4 : 2;
     constexpr bool kF64 = sizeof(T) == 8;
@@ -192,6 +205,24 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
             else { wx[c][0] = 1.f - static_cast<float>(txd[c]); wx[c][1] = static_cast<float>(txd[c]); wx[c][2] = 0.f; wx[c][3] = 0.f; }
         }
     }
+    int w0 = 0;                                                    // WIN: first window word (box column, even)
+    float w5[WIN ? COLS : 1][5];
+    if constexpr (WIN > 0) {
+        int lo = ox[0];
+#pragma unroll
+        for (int c = 1; c < COLS; ++c) {
+            if (Ic + c >= W) ox[c] = ox[c - 1];                    // columns past the lattice: inside the window, never stored
+            lo = min(lo, ox[c]);
+        }
+        w0 = lo & ~1;
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) {
+            const int k = ox[c] - w0 - (WIN == 2 ? c / 2 : c);     // 0 or 1 (host-checked: window_mode)
+#pragma unroll
+            for (int j = 0; j < 5; ++j)
+                w5[c][j] = k == 0 ? (j < 4 ? wx[c][j < 4 ? j : 0] : 0.f) : (j >= 1 ? wx[c][j >= 1 ? j - 1 : 0] : 0.f);
+        }
+    }
 
     if (p.use_tma) {
         mbar_wait(&bar, 0);
@@ -233,6 +264,29 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     T probe = 0;
     int probe_hi = 0;
     auto hrow = [&](const T* r, T (&dst)[COLS]) {
+        if constexpr (WIN > 0) {
+            const float* const rp = reinterpret_cast<const float*>(r) + w0;
+            float win[WN];
+            const float2 a = *reinterpret_cast<const float2*>(rp);
+            win[0] = a.x; win[1] = a.y;
+            if constexpr (WIN == 1) {
+                const float4 b = *reinterpret_cast<const float4*>(rp + 2);
+                const float2 d = *reinterpret_cast<const float2*>(rp + 6);
+                win[2] = b.x; win[3] = b.y; win[4] = b.z; win[5] = b.w; win[6] = d.x; win[7] = d.y;
+            } else {
+                const float2 b = *reinterpret_cast<const float2*>(rp + 2);
+                const float2 d = *reinterpret_cast<const float2*>(rp + 4);
+                win[2] = b.x; win[3] = b.y; win[4] = d.x; win[5] = d.y;
+            }
+#pragma unroll
+            for (int c = 0; c < COLS; ++c) {
+                constexpr int kHalf = WIN == 2 ? 2 : 1;
+                const int sc = c / kHalf;
+                dst[c] = fmaf(w5[c][4], win[sc + 4], fmaf(w5[c][3], win[sc + 3], fmaf(w5[c][2], win[sc + 2], fmaf(w5[c][1], win[sc + 1], w5[c][0] * win[sc]))));
+                probe += dst[c];
+            }
+            return;
+        }
 #pragma unroll
         for (int c = 0; c < COLS; ++c) {
             const T* q = r + ox[c];
@@ -248,9 +302,19 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     };
     // one output row from the window; `ph` = slot holding the window's first row (a constant once the
     // phase loop below is unrolled, so the window never moves between registers)
+    // FP64 bicubic: the Catmull-Rom coefficients of the vertical pass depend on the window only -- formed once per window
+    // position, shared by the f_lat output rows under it (same operations, same bits: exact.cuh)
+    CatmullCoef vk[kF64 && kCubic ? COLS : 1];
     auto emit = [&](int jr, const T (&h)[TAPS][COLS], int ph) {
         T v[COLS];
-        if constexpr (kF64) {
+        if constexpr (kF64 && kCubic) {
+            const double2 ty2 = s_ty[jr];
+#pragma unroll
+            for (int c = 0; c < COLS; ++c) {
+                v[c] = catmull_rom_eval(vk[c], h[(ph + 1) % TAPS][c], ty2.x, ty2.y);
+                probe_hi = max(probe_hi, __double2hiint(v[c]) & 0x7fffffff);
+            }
+        } else if constexpr (kF64) {
             const double2 ty2 = s_ty[jr];
             const double ty = ty2.x;
 #pragma unroll
@@ -290,6 +354,11 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     for (;;) {
 #pragma unroll
         for (int ph = 0; ph < TAPS; ++ph) {                        // slot (ph+k)%TAPS holds tile row top+k
+            if constexpr (kF64 && kCubic) {                        // at every window position (formed lazily, inside the loop
+#pragma unroll                                                     // below, it LOST 7 %: profiles/r02_upsample_small_factor_ab.txt)
+                for (int c = 0; c < COLS; ++c)
+                    vk[c] = catmull_rom_coef(h[ph % TAPS][c], h[(ph + 1) % TAPS][c], h[(ph + 2) % TAPS][c], h[(ph + 3) % TAPS][c]);
+            }
 #pragma unroll 1
             while (jr < jr_end && s_top[jr] == top) {              // uniform across the row group
                 emit(jr, h, ph);
@@ -404,6 +473,36 @@ static int max_span(const int* h_base, int64_t begin, int64_t end, int tile, int
     return worst;
 }
 
+// Does every group of four adjacent output columns (one thread of the tiled kernel) fit the window-load form of the FP32
+// bicubic kernel?  Mirrors the kernel's own arithmetic: tap start of column c = base - 1 (columns past the lattice inherit
+// their left neighbour's), window start = the smallest of the four rounded down to even, shift k_c = start_c - window - s_c
+// with s_c = c / 2 (mode 2: longitude factor 2) or c (mode 1: factor 1) must be 0 or 1.  Box starts are multiples of four
+// columns, so parities agree between global and box columns.  Returns 2, 1 or 0 (generic kernel).
+static int window_mode(const AxisTables& lon) {
+    static const bool off = getenv("AUVI_NO_WINDOW") != nullptr;  // A/B measurements only
+    if (off) return 0;
+    if (lon.window_mode_cache && *lon.window_mode_cache >= 0) return *lon.window_mode_cache;
+    int verdict = 0;
+    for (int mode = 2; mode >= 1 && !verdict; --mode) {
+        bool ok = true;
+        for (int g = 0; g < lon.n && ok; g += 4) {
+            int start[4], lo = 0;
+            for (int c = 0; c < 4; ++c) {
+                start[c] = g + c < lon.n ? lon.h_base[g + c] - 1 : start[c - 1];
+                lo = c == 0 || start[c] < lo ? start[c] : lo;
+            }
+            const int w0 = lo & ~1;
+            for (int c = 0; c < 4; ++c) {
+                const int k = start[c] - w0 - (mode == 2 ? c / 2 : c);
+                ok = ok && (k == 0 || k == 1);
+            }
+        }
+        if (ok) verdict = mode;
+    }
+    if (lon.window_mode_cache) *lon.window_mode_cache = verdict;
+    return verdict;
+}
+
 template <typename T, int METHOD>
 static cudaError_t launch_tiled(const GridDesc& d, const AxisTables& lat, const AxisTables& lon, int64_t row_begin,
                                 int64_t row_end, void* out, int64_t out_ld, cudaStream_t st, LaunchInfo* info) {
@@ -455,16 +554,25 @@ static cudaError_t launch_tiled(const GridDesc& d, const AxisTables& lat, const 
     // grid are patched to the clamped edge row inside the kernel.
     p.use_tma = make_grid_tensor_map(d, bw, bh, &tmap) ? 1 : 0;
 
-    const size_t smem = static_cast<size_t>(slabs) * p.box_stride * es;
+    size_t smem = static_cast<size_t>(slabs) * p.box_stride * es;
     auto kern = upsample_tiled_kernel<T, METHOD>;
-    if (smem > 48 * 1024) {
+    int win = 0;
+    if constexpr (sizeof(T) == 4 && METHOD == CUBIC) {
+        win = window_mode(lon);
+        if (win == 2) kern = upsample_tiled_kernel<T, METHOD, 2>;
+        if (win == 1) kern = upsample_tiled_kernel<T, METHOD, 1>;
+        if (win) smem += 32;                                       // a window may end a few words past its thread's last tap
+    }
+    // the 48 KB a kernel gets without opting in count its STATIC shared memory (2.7 KB here) too: a dynamic size of 46-48 KB
+    // used to fail the launch with "invalid argument" (found by test_lattice_f32_bicubic_window_loads: 64 x 300, 3 x 2)
+    if (smem > 40 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
     }
     dim3 grid(static_cast<unsigned>((lon.n + tile_cols - 1) / tile_cols),
               static_cast<unsigned>((row_end - row_begin + tj - 1) / tj));
     kern<<<grid, kTileThreads, smem, st>>>(tmap, p);
-    if (info) { info->launches += 1; info->used_tma = p.use_tma; }
+    if (info) { info->launches += 1; info->used_tma = p.use_tma; info->used_window = win; }
     return cudaGetLastError();
 }
 

@@ -76,6 +76,7 @@ SYMBOLS = {
     "auvi_last_kernel_ms": (C.c_float, [_vp]),
     "auvi_launch_count": (_i64, []),
     "auvi_uses_tma": (_i32, [_vp]),
+    "auvi_uses_window": (_i32, [_vp]),
     "auvi_device_count": (_i32, []),
     "auvi_version": (_i32, []),
 }
@@ -293,6 +294,10 @@ class Grid:
     @property
     def uses_tma(self):
         return bool(load().auvi_uses_tma(self._h))
+
+    @property
+    def uses_window(self):
+        return int(load().auvi_uses_window(self._h))
 
 
 def error_metrics_device(truth_ptr, est_ptr, dtype, n, stream=None):

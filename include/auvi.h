@@ -236,6 +236,8 @@ const char* auvi_last_error(void);          /* thread-local message of the last 
 float auvi_last_kernel_ms(const auvi_grid* g); /* device time of the kernels of the last synchronous call */
 int64_t auvi_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 int auvi_uses_tma(const auvi_grid* g);      /* 1 if the last lattice launch staged tiles by TMA */
+int auvi_uses_window(const auvi_grid* g);   /* window-load form of the FP32 bicubic kernel in the last lattice launch: 0 = generic,
+                                               1 / 2 = the form for longitude factor 1 / 2 (csrc/upsample.cu) */
 int auvi_device_count(void);                /* CUDA devices visible (0 when none: compute calls fail) */
 int auvi_version(void);
 

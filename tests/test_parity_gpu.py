@@ -230,6 +230,35 @@ def test_lattice_f32_within_tolerance(auvi, f):
     g.close()
 
 
+@pytest.mark.parametrize("n_lat,n_lon,f_lat,f_lon,holes,bounds", [
+    (200, 700, 2, 2, 0, (-180.0, -160.0, 20.0, 30.0)),     # noisy node columns: floor() one below on ~half of them
+    (200, 701, 2, 2, 40, (-180.0, -160.0, 20.0, 30.0)),    # NaN holes: zero-weight window words that are NaN -> exact re-evaluation
+    (90, 1500, 4, 1, 0, (-180.0, -160.0, 20.0, 30.0)),     # longitude factor 1: eight-word windows, three tiles wide
+    (90, 1027, 4, 1, 30, (0.0, 1.0, 0.0, 1.0)),            # noise-free axis, ragged last thread
+    (150, 515, 1, 2, 10, (100.0, 110.0, -10.0, 0.0)),
+    (64, 300, 3, 2, 5, (-30.9967, -29.4993, -0.5035, 1.0071)),
+])
+def test_lattice_f32_bicubic_window_loads(auvi, n_lat, n_lon, f_lat, f_lon, holes, bounds):
+    """The window-load form of the FP32 bicubic kernel (longitude factors 1 and 2: vector shared-memory loads + five shifted
+    weights per column, csrc/upsample.cu) against the FP64 oracle on every cell, and that it is the form that ran; the same
+    grids through a longitude factor the form does not cover take the generic kernel."""
+    z = ob.synth_grid(n_lat, n_lon).astype(np.float32)
+    if holes:
+        z.ravel()[np.random.RandomState(11).choice(z.size, holes, replace=False)] = np.nan
+    pts, nn_lat, nn_lon = ob.lattice_queries(n_lat, n_lon, *bounds, f_lat=f_lat, f_lon=f_lon)
+    orc = ob.Oracle(z.astype(np.float64), *bounds)
+    g = auvi.Grid(z, *bounds)
+    got = g.lattice(auvi.CUBIC, auvi.AXIS_EXPANDED, f_lat, f_lon)
+    assert g.uses_window == (1 if f_lon == 1 else 2), "expected the window-load kernel"
+    want = orc.batch(ob.CUBIC, pts).reshape(nn_lat, nn_lon)
+    _close(got.astype(np.float64), want)
+    g.lattice(auvi.CUBIC, auvi.AXIS_EXPANDED, f_lat, 4)
+    assert g.uses_window == 0
+    g.lattice(auvi.BILINEAR, auvi.AXIS_EXPANDED, f_lat, f_lon)
+    assert g.uses_window == 0
+    g.close()
+
+
 @pytest.mark.parametrize("name,frac", [("mid_atlantic", 0.5), ("mariana", 0.5), ("mid_atlantic", 0.9)])
 def test_gap_fill_nodes_matches_oracle(auvi, torch, name, frac):
     """Grid-B as a full-grid fill: every masked cell gets method(node query); valid cells pass through."""
