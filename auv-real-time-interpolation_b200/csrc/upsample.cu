@@ -108,7 +108,10 @@ __device__ __noinline__ T lattice_cell_exact(const TileParams<T>* p, int64_t J, 
 // (window_mode) and launches the generic form otherwise.  A zero weight on a NaN tap yields NaN: such an output goes to the
 // exact re-evaluation like any other dirty one.
 template <typename T, int METHOD, int WIN = 0>
-__global__ void __launch_bounds__(kTileThreads, sizeof(T) == 4 ? 4 : 3)
+#ifndef AUVI_F64_MINB
+#define AUVI_F64_MINB 3
+#endif
+__global__ void __launch_bounds__(kTileThreads, sizeof(T) == 4 ? 4 : AUVI_F64_MINB)
 upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileParams<T> p) {
     constexpr bool kCubic = (METHOD == CUBIC);
     static_assert(WIN == 0 || (METHOD == CUBIC && sizeof(T) == 4), "window loads: FP32 bicubic only");
@@ -122,8 +125,8 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* tile = reinterpret_cast<T*>(smem_raw);                      // [bh][bw]
     __shared__ uint64_t bar;
-    __shared__ int s_top[kTileRowsMax];                            // local row of the first tap
-    __shared__ double2 s_ty[kF64 ? kTileRowsMax : 1];              // frac(pos_y) (NaN if out of bounds) and half of it
+    __shared__ int s_top[kTileRowsMax + 1];                            // local row of the first tap
+    __shared__ double2 s_ty[kF64 ? kTileRowsMax + 1 : 1];              // frac(pos_y) (NaN if out of bounds) and half of it
     __shared__ float4 s_wy[kF64 ? 1 : kTileRowsMax];               // FP32 vertical tap weights
 
     const int tid = threadIdx.x;
@@ -285,8 +288,7 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                 dst[c] = fmaf(w5[c][4], win[sc + 4], fmaf(w5[c][3], win[sc + 3], fmaf(w5[c][2], win[sc + 2], fmaf(w5[c][1], win[sc + 1], w5[c][0] * win[sc]))));
                 probe += dst[c];
             }
-            return;
-        }
+        } else {
 #pragma unroll
         for (int c = 0; c < COLS; ++c) {
             const T* q = r + ox[c];
@@ -299,16 +301,23 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
             }
             if constexpr (!kF64) probe += dst[c];
         }
+        }
     };
     // one output row from the window; `ph` = slot holding the window's first row (a constant once the
     // phase loop below is unrolled, so the window never moves between registers)
     // FP64 bicubic: the Catmull-Rom coefficients of the vertical pass depend on the window only -- formed once per window
     // position, shared by the f_lat output rows under it (same operations, same bits: exact.cuh)
     CatmullCoef vk[kF64 && kCubic ? COLS : 1];
+    // FP64 bicubic: s_ty[jr] / s_top[jr] are loaded one output row ahead, which takes the shared-memory latency out of the
+    // dependent chain load -> multiply chain -> store of a row (2x1: 0.70 -> 0.78 of the HBM peak, 4x4: 0.93 -> 0.96, 2x2: 0.81 -> 0.82,
+    // profiles/r02_upsample_small_factor_ab.txt)
+    double2 ty_next = make_double2(0.0, 0.0);
+    int top_next = 0;
     auto emit = [&](int jr, const T (&h)[TAPS][COLS], int ph) {
         T v[COLS];
         if constexpr (kF64 && kCubic) {
-            const double2 ty2 = s_ty[jr];
+            const double2 ty2 = ty_next;
+            ty_next = s_ty[jr + 1]; top_next = s_top[jr + 1];      // one entry of slack behind the last row
 #pragma unroll
             for (int c = 0; c < COLS; ++c) {
                 v[c] = catmull_rom_eval(vk[c], h[(ph + 1) % TAPS][c], ty2.x, ty2.y);
@@ -347,6 +356,7 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     T h[TAPS][COLS];
     int jr = jr_begin;
     int top = s_top[jr];                                           // window = tile rows [top, top+TAPS)
+    if constexpr (kF64 && kCubic) { ty_next = s_ty[jr]; top_next = top; }
     const T* next_row = my_tile + top * bw;
 #pragma unroll
     for (int k = 0; k < TAPS; ++k, next_row += bw) hrow(next_row, h[k]);
@@ -358,11 +368,17 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
 #pragma unroll                                                     // below, it LOST 7 %: profiles/r02_upsample_small_factor_ab.txt)
                 for (int c = 0; c < COLS; ++c)
                     vk[c] = catmull_rom_coef(h[ph % TAPS][c], h[(ph + 1) % TAPS][c], h[(ph + 2) % TAPS][c], h[(ph + 3) % TAPS][c]);
-            }
 #pragma unroll 1
-            while (jr < jr_end && s_top[jr] == top) {              // uniform across the row group
-                emit(jr, h, ph);
-                ++jr;
+                while (jr < jr_end && top_next == top) {           // uniform across the row group
+                    emit(jr, h, ph);
+                    ++jr;
+                }
+            } else {
+#pragma unroll 1
+                while (jr < jr_end && s_top[jr] == top) {          // uniform across the row group
+                    emit(jr, h, ph);
+                    ++jr;
+                }
             }
             if (jr >= jr_end) goto swept;
             hrow(next_row, h[ph]);                                 // the oldest slot takes tile row top+TAPS
@@ -510,7 +526,8 @@ static cudaError_t launch_tiled(const GridDesc& d, const AxisTables& lat, const 
     const int lo = METHOD == CUBIC ? 1 : 0;
     const size_t es = sizeof(T);
     const int align = static_cast<int>(16 / es);
-    int tj = kTileRowsMax;
+    static const int tj_cap = getenv("AUVI_TILE_ROWS") ? atoi(getenv("AUVI_TILE_ROWS")) : kTileRowsMax;   // A/B measurements only
+    int tj = tj_cap >= 16 && tj_cap <= kTileRowsMax ? tj_cap : kTileRowsMax;
     const int tile_cols = kColThreads * align;
     int slabs = 1;
     int bw = max_span(lon.h_base, 0, lon.n, tile_cols, taps, lo, align);

@@ -19,7 +19,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-LIB_PATH = os.path.join(PKG, "lib", "libauvi.so")
+LIB_PATH = os.environ.get("AUVI_LIB") or os.path.join(PKG, "lib", "libauvi.so")   # AUVI_LIB: another build of the same library (A/B runs)
 
 BILINEAR, CUBIC, KRIGING, NN, IDW, BILINEAR_SEARCH, IDW_KNN, KRIGING_FITTED = 0, 1, 2, 3, 4, 5, 6, 7
 METHOD_NAMES = {BILINEAR: "bilinear", CUBIC: "cubic", KRIGING: "kriging", NN: "nn", IDW: "idw",
