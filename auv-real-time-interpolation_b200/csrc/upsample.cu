@@ -127,7 +127,7 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     __shared__ uint64_t bar;
     __shared__ int s_top[kTileRowsMax + 1];                            // local row of the first tap
     __shared__ double2 s_ty[kF64 ? kTileRowsMax + 1 : 1];              // frac(pos_y) (NaN if out of bounds) and half of it
-    __shared__ float4 s_wy[kF64 ? 1 : kTileRowsMax];               // FP32 vertical tap weights
+    __shared__ float4 s_wy[kF64 ? 1 : kTileRowsMax + 1];               // FP32 vertical tap weights
 
     const int tid = threadIdx.x;
     const int W = p.lon.n;
@@ -313,6 +313,10 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     // profiles/r02_upsample_small_factor_ab.txt)
     double2 ty_next = make_double2(0.0, 0.0);
     int top_next = 0;
+    // The same for the FP32 window-load kernel of longitude factor 1 (2x1 0.84 -> 0.91, 1x1 0.72 -> 0.77, 4x1 0.97 -> 0.99); the
+    // factor-2 form LOSES with it (2x2 0.98 -> 0.94: eight more spill bytes inside its loop), so it keeps loading in place.
+    constexpr bool kAheadF32 = WIN == 1;
+    [[maybe_unused]] float4 wy_next = make_float4(0.f, 0.f, 0.f, 0.f);
     auto emit = [&](int jr, const T (&h)[TAPS][COLS], int ph) {
         T v[COLS];
         if constexpr (kF64 && kCubic) {
@@ -334,7 +338,9 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                 probe_hi = max(probe_hi, __double2hiint(v[c]) & 0x7fffffff);
             }
         } else {
-            const float4 w = s_wy[jr];
+            float4 w;
+            if constexpr (kAheadF32) { w = wy_next; wy_next = s_wy[jr + 1]; top_next = s_top[jr + 1]; }
+            else w = s_wy[jr];
             probe += w.x;
 #pragma unroll
             for (int c = 0; c < COLS; ++c) {
@@ -357,6 +363,7 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     int jr = jr_begin;
     int top = s_top[jr];                                           // window = tile rows [top, top+TAPS)
     if constexpr (kF64 && kCubic) { ty_next = s_ty[jr]; top_next = top; }
+    if constexpr (kAheadF32) { wy_next = s_wy[jr]; top_next = top; }
     const T* next_row = my_tile + top * bw;
 #pragma unroll
     for (int k = 0; k < TAPS; ++k, next_row += bw) hrow(next_row, h[k]);
@@ -370,6 +377,12 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                     vk[c] = catmull_rom_coef(h[ph % TAPS][c], h[(ph + 1) % TAPS][c], h[(ph + 2) % TAPS][c], h[(ph + 3) % TAPS][c]);
 #pragma unroll 1
                 while (jr < jr_end && top_next == top) {           // uniform across the row group
+                    emit(jr, h, ph);
+                    ++jr;
+                }
+            } else if constexpr (kAheadF32) {
+#pragma unroll 1
+                while (jr < jr_end && top_next == top) {
                     emit(jr, h, ph);
                     ++jr;
                 }
