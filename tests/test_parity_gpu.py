@@ -305,6 +305,7 @@ def test_row_slabs_equal_whole_grid(auvi, torch, ld):
     dz[:, :260] = torch.from_numpy(z).cuda()
     halo = 12
     for meth, kind, f, fill in ((auvi.CUBIC, auvi.AXIS_EXPANDED, 4, 0), (auvi.BILINEAR, auvi.AXIS_EXPANDED, 4, 0),
+                                (auvi.CUBIC, auvi.AXIS_EXPANDED, 2, 0),      # the window-load kernel on slabs
                                 (auvi.IDW, auvi.AXIS_NODES, 1, 1), (auvi.KRIGING, auvi.AXIS_NODES, 1, 1)):
         ref = whole.lattice(meth, kind, f, f, fill=fill)
         out_rows = ref.shape[0]
