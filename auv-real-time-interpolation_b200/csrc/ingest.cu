@@ -65,19 +65,26 @@ mask_cells_kernel(T* __restrict__ z, int64_t ld, int n_lon, int row0, int rows, 
     }
 }
 
+// A work item is 1024 consecutive cells of one row: one division per item, none per cell (a 65536^2 grid is 4.3 G cells).
 template <typename T>
 __global__ void __launch_bounds__(256)
 mask_hash_kernel(T* __restrict__ z, int64_t ld, int n_lon, int row0, int rows, uint64_t threshold, uint64_t seed,
                  unsigned long long* __restrict__ n_masked) {
-    const int64_t total = static_cast<int64_t>(rows) * n_lon;
+    constexpr int kChunk = 1024;
+    const int chunks = (n_lon + kChunk - 1) / kChunk;
+    const int64_t items = static_cast<int64_t>(rows) * chunks;
+    const uint64_t salt = seed * 0xD1342543DE82EF95ull;
     unsigned long long mine = 0;
-    for (int64_t k = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; k < total; k += static_cast<int64_t>(gridDim.x) * 256) {
-        const int64_t r = k / n_lon;
-        const int c = static_cast<int>(k - r * n_lon);
-        const uint64_t flat = static_cast<uint64_t>(r + row0) * static_cast<uint64_t>(n_lon) + c;   // GLOBAL index
-        if ((splitmix64(flat ^ (seed * 0xD1342543DE82EF95ull)) >> 11) < threshold) {
-            z[r * ld + c] = static_cast<T>(qnan());
-            ++mine;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+        const int64_t r = it / chunks;
+        const int c_lo = static_cast<int>(it - r * chunks) * kChunk, c_hi = min(n_lon, c_lo + kChunk);
+        const uint64_t flat0 = static_cast<uint64_t>(r + row0) * static_cast<uint64_t>(n_lon);   // GLOBAL index of the row's first cell
+        T* const zr = z + r * ld;
+        for (int c = c_lo + static_cast<int>(threadIdx.x); c < c_hi; c += 256) {
+            if ((splitmix64((flat0 + c) ^ salt) >> 11) < threshold) {
+                zr[c] = static_cast<T>(qnan());
+                ++mine;
+            }
         }
     }
     if (n_masked) {

@@ -27,3 +27,14 @@ t0 = time.perf_counter()
 for _ in range(reps): res = auvi.error_metrics_device(truth.data_ptr(), out.data_ptr(), auvi.F32, n * n, st)
 ms = (time.perf_counter() - t0) / reps * 1e3
 print(f"error metrics n={n}^2 elements: {ms:8.3f} ms per call  {n*n*8/ms/1e6/peak:5.2f} of HBM peak (8 B/element)  mae={res[0]:.6g} rmse={res[1]:.6g} max={res[2]:.6g} n_nan={res[3]}")
+# the counter-hash mask (auvi_grid_mask_hash): writes NaN into `frac` of the cells, no reads
+zz = truth.clone()
+gm = auvi.Grid(adopt=dict(ptr=zz.data_ptr(), dtype=auvi.F32, n_lat=n, n_lon=n, ld=n, row0=0, rows=n, keep=zz), min_lon=100.0, max_lon=110.0, min_lat=-10.0, max_lat=0.0)
+gm.mask_hash(frac, seed=42, count=False, stream=st); torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(reps): gm.mask_hash(frac, seed=42, count=False, stream=st)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+import hashlib
+print(f"mask_hash n={n} frac={frac:.2f}: {ms:8.3f} ms  {n*n/ms/1e6:8.1f} Gcells/s  masked={int(torch.isnan(zz).sum())}  sha1={hashlib.sha1(torch.isnan(zz).cpu().numpy().tobytes()).hexdigest()[:12] if n <= 8192 else '-'}")
