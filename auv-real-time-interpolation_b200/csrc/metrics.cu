@@ -219,9 +219,11 @@ variogram_partial_kernel(const T* __restrict__ z, int64_t ld, int rows, int n_lo
     double acc[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0.0;
-    const int64_t total = static_cast<int64_t>(rows) * n_lon;
-    for (int64_t c = static_cast<int64_t>(blockIdx.x) * kMetBlock + threadIdx.x; c < total; c += static_cast<int64_t>(gridDim.x) * kMetBlock) {
-        const int r = static_cast<int>(c / n_lon), i = static_cast<int>(c - static_cast<int64_t>(r) * n_lon);
+    const int chunks = (n_lon + kMetBlock - 1) / kMetBlock;       // work item: kMetBlock consecutive cells of one row
+    const int64_t items = static_cast<int64_t>(rows) * chunks;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+        const int r = static_cast<int>(it / chunks), i = static_cast<int>(it - static_cast<int64_t>(r) * chunks) * kMetBlock + static_cast<int>(threadIdx.x);
+        if (i >= n_lon) continue;
         const double v = static_cast<double>(__ldg(z + static_cast<int64_t>(r) * ld + i));
         if (isnan(v)) continue;
 #pragma unroll
