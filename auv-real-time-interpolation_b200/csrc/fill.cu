@@ -876,6 +876,45 @@ constexpr int kBBW = kBW + 2 * kBHaloC;        // 136
 constexpr int kBBH = kBH + 2 * kBHaloR;        // 36
 constexpr int kBThreads = 256;
 
+// mean_valid4 (exact.cuh, GridH.cpp:10-18) without branches, for the streaming kernel below where every lane takes it with
+// its own count: the sum gathers the valid corners in the order a, b, c, d by predicated adds; the division by the count
+// is the product with 1 / n -- exact for n = 1, 2, 4, and for n = 3 the same Markstein step as div_count (r = s - 3q exact
+// in an FMA, q' = RN(q + r * RN(1/3)) is the correctly rounded quotient), which leaves q alone when r = 0.  Same bits.
+__device__ __forceinline__ void add_if_number(double& s, float v) {
+    const double vd = static_cast<double>(v);
+    asm("{\n\t.reg .pred p;\n\tsetp.num.f32 p, %1, %1;\n\t@p add.rn.f64 %0, %0, %2;\n\t}" : "+d"(s) : "f"(v), "d"(vd));
+}
+__device__ __forceinline__ void add_if_number(double& s, double v) {
+    asm("{\n\t.reg .pred p;\n\tsetp.num.f64 p, %1, %1;\n\t@p add.rn.f64 %0, %0, %1;\n\t}" : "+d"(s) : "d"(v));
+}
+__device__ __noinline__ double ddiv_cold(double a, double b) { return ddiv(a, b); }   // out of line: never speculated into the stream
+template <typename T>
+__device__ __forceinline__ double mean_valid4_flat(T a, T b, T c, T d) {
+    const int n = static_cast<int>(a == a) + static_cast<int>(b == b) + static_cast<int>(c == c) + static_cast<int>(d == d);
+    double s = 0.0;
+    add_if_number(s, a); add_if_number(s, b); add_if_number(s, c); add_if_number(s, d);
+    const int e = (n >> 1) << 20;                                  // n = 1, 2, 4 -> exponent steps 0, 1, 2
+    const double inv = n == 3 ? 0.33333333333333331 : __hiloint2double(0x3ff00000 - e, 0);
+    const double cnt = n == 3 ? 3.0 : __hiloint2double(0x3ff00000 + e, 0);
+    double q = dmul(s, inv);
+    const double r = __fma_rn(-cnt, q, s);
+    q = __fma_rn(r, inv, q);
+    const double mag = fabs(s);
+    if (!(mag > 1e-280 && mag < 1e300) && s != 0.0) q = ddiv_cold(s, cnt);   // where q or r could go subnormal / overflow: the division itself
+    return n ? q : qnan();
+}
+
+constexpr int kNoCell = -(1 << 30);            // x0 table entry of a query whose position is NaN (out of bounds)
+
+// The three lerps of GridH.cpp:200-209 in the reference's order.  Out of line: a gap fill never gets here (see the kernel).
+__device__ __noinline__ double bilinear_lerp_cold(double a, double b, double c, double d, double x, double y, int x0, int y0) {
+    const double wx = dsub(x, __int2double_rn(x0)), wy = dsub(y, __int2double_rn(y0));
+    const double ux = dsub(1.0, wx);
+    const double lo = dadd(dmul(ux, a), dmul(wx, b));
+    const double hi = dadd(dmul(ux, c), dmul(wx, d));
+    return dadd(dmul(dsub(1.0, wy), lo), dmul(wy, hi));
+}
+
 template <typename T>
 struct BilinSmem {
     alignas(128) T tile[2][kBBH * kBBW];
@@ -924,8 +963,9 @@ bilinear_fill_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         if (tid < kBW) {
             const int I = I0 + tid;
             const bool in = I < p.n_out_cols;
-            s.x[tid] = in ? __ldg(p.lon.pos + I) : qnan();
-            s.x0[tid] = in ? __ldg(p.lon.base + I) : 0;
+            const double x = in ? __ldg(p.lon.pos + I) : qnan();
+            s.x[tid] = x;
+            s.x0[tid] = isnan(x) ? kNoCell : __ldg(p.lon.base + I);
         } else if (tid < kBW + kBH) {
             const int t = tid - kBW;
             const bool in = J0 + t < p.row_end;
@@ -947,26 +987,26 @@ bilinear_fill_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
             else { const double2 q = *reinterpret_cast<const double2*>(src); v[0] = q.x; v[1] = q.y; }
             const double y = s.y[lj];
             const int y0 = s.y0[lj], y1 = min(y0 + 1, p.g.n_lat - 1);
+            const T* const r0p = tl + (y0 - r0) * kBBW - c0;
+            const T* const r1p = tl + (y1 - r0) * kBBW - c0;
+            const bool y_ok = !isnan(y);
 #pragma unroll
             for (int c = 0; c < VEC; ++c) {
                 if (v[c] == v[c]) continue;                         // valid cell: passes through
                 const int li = col + c;
-                const double x = s.x[li];
+                const int x0 = s.x0[li];                            // kNoCell: the query is out of bounds (x is NaN)
                 double result = qnan();
-                if (!isnan(x) && !isnan(y)) {
-                    const int x0 = s.x0[li], x1 = min(x0 + 1, p.g.n_lon - 1);
-                    const double wx = dsub(x, __int2double_rn(x0)), wy = dsub(y, __int2double_rn(y0));
-                    const T* const r0p = tl + (y0 - r0) * kBBW - c0;
-                    const T* const r1p = tl + (y1 - r0) * kBBW - c0;
-                    const double a = static_cast<double>(r0p[x0]), b = static_cast<double>(r0p[x1]);
-                    const double cc = static_cast<double>(r1p[x0]), d = static_cast<double>(r1p[x1]);
-                    if (isnan(a) || isnan(b) || isnan(cc) || isnan(d)) result = mean_valid4(a, b, cc, d);
-                    else {
-                        const double ux = dsub(1.0, wx);
-                        const double lo = dadd(dmul(ux, a), dmul(wx, b));
-                        const double hi = dadd(dmul(ux, cc), dmul(wx, d));
-                        result = dadd(dmul(dsub(1.0, wy), lo), dmul(wy, hi));
-                    }
+                if (y_ok && x0 != kNoCell) {
+                    const int x1 = min(x0 + 1, p.g.n_lon - 1);
+                    const T a = r0p[x0], b = r0p[x1], cc = r1p[x0], d = r1p[x1];
+                    // A masked cell queried at its own node is one of its four corners (floor() of the node position is the
+                    // node or, by FP64 noise, the one below: SURVEY.md section 0 fact 3), so this is the NaN-corner mean
+                    // (GridH.cpp:186-198) for every query of a gap fill; the lerp stays reachable, out of line.
+                    if (a != a || b != b || cc != cc || d != d)
+                        result = mean_valid4_flat<T>(a, b, cc, d);
+                    else
+                        result = bilinear_lerp_cold(static_cast<double>(a), static_cast<double>(b), static_cast<double>(cc), static_cast<double>(d),
+                                                    s.x[li], y, x0, y0);
                 }
                 v[c] = static_cast<T>(result);
             }
