@@ -502,13 +502,22 @@ def run_upsample(c):
                           max(3, args.steps // 2), 2)
         ups["bicubic_latitude_only"] = {"Mcells_per_s": out_rows * n_lon / (ms_l * 1e-3) / 1e6, "ms": ms_l,
                                         "hbm_frac": 5.0 * out_rows * n_lon / (ms_l * 1e-3) / 1e9 / c.peak}
+        # the 2x lattice of the same grid (the factor the reference's driver uses): window-load form of the FP32 bicubic kernel,
+        # 4 + 4/4 = 5 B per output cell
+        r2, c2 = 2 * (n_lat - 1) + 1, 2 * (n_lon - 1) + 1
+        ld2 = (c2 + 3) // 4 * 4
+        out2 = out.view(-1)[: r2 * ld2].view(r2, ld2)
+        for name2, meth2 in (("bicubic_2x", auvi.CUBIC), ("bilinear_2x", auvi.BILINEAR)):
+            ms2, _ = c.timed(lambda: g.lattice_device(meth2, auvi.AXIS_EXPANDED, 2, 2, 0, 0, r2, out2.data_ptr(), ld2, None, c.stream),
+                             max(3, args.steps // 4), 2)
+            ups[name2] = {"Mcells_per_s": r2 * c2 / (ms2 * 1e-3) / 1e6, "ms": ms2, "hbm_frac": 5.0 * r2 * c2 / (ms2 * 1e-3) / 1e9 / c.peak}
         methods["upsample_4x_16384sq_f32 (configs[3])"] = ups
         del out
         torch.cuda.empty_cache()
         methods.update(methods_gap_fill(c))
         methods["mariana_50pct_point_list (configs[1])"] = methods_mariana(c)
         extra.update(extra_grid_a_points(c))
-        extra.update(extra_grid_a_lattice(c))
+        methods["grid_a_2x_lattice_4000x3200_f64 (configs[0])"] = extra_grid_a_lattice(c)
         extra["reference_gpu_sm100a"] = extra_reference_gpu(c)
 
     cpu = None
@@ -547,12 +556,15 @@ def methods_gap_fill(c):
         tab = {}
         for name, meth in methods:
             fn = lambda: g.lattice_device(meth, auvi.AXIS_NODES, 1, 1, 1, 0, n, out.data_ptr(), n, None, c.stream)
-            ms, _ = c.timed(fn, 3, 1)
+            ms, _ = c.timed(fn, 5 if n <= 16384 else 3, 2)
             row = {"Mcells_per_s": n * n / (ms * 1e-3) / 1e6, "ms": ms, "hbm_frac": FILL_BYTES_PER_CELL * n * n / (ms * 1e-3) / 1e9 / c.peak,
                    "nan_left": int(torch.isnan(out).sum().item())}
             if truth is not None:
+                t0 = time.perf_counter()
                 mae, rmse, mx, n_nan, cnt = g.fill_metrics_device(out.data_ptr(), n, truth.data_ptr(), n, 0, n, c.stream)
-                row.update({"rmse_m": rmse, "mae_m": mae, "max_m": mx, "filled_cells": cnt})
+                t_met = (time.perf_counter() - t0) * 1e3           # synchronous call: two kernels + the read-back (csrc/metrics.cu)
+                row.update({"rmse_m": rmse, "mae_m": mae, "max_m": mx, "filled_cells": cnt,
+                            "metrics_call_ms": t_met, "metrics_hbm_frac": 12.0 * n * n / (t_met * 1e-3) / 1e9 / c.peak})
             if name == "idw":
                 row["note"] = IDW_NOTE
                 if pipes:
@@ -630,7 +642,7 @@ def extra_grid_a_lattice(c):
                        ("idw", auvi.IDW)):
         fn = lambda: g.lattice_device(meth, auvi.AXIS_EXPANDED, 2, 2, 0, 0, rows, out.data_ptr(), 8000, None, c.stream)
         ms, _ = c.timed(fn, 5, 1)
-        res[f"grid_a_2x_lattice_f64_{name}"] = {"Mcells_per_s": rows * cols / (ms * 1e-3) / 1e6, "ms": ms,
+        res[name] = {"Mcells_per_s": rows * cols / (ms * 1e-3) / 1e6, "ms": ms,
                                                  "hbm_frac": 10.0 * rows * cols / (ms * 1e-3) / 1e9 / c.peak}
     g.close()
     return res
