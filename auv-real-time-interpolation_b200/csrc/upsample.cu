@@ -312,6 +312,12 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     // dependent chain load -> multiply chain -> store of a row (2x1: 0.70 -> 0.78 of the HBM peak, 4x4: 0.93 -> 0.96, 2x2: 0.81 -> 0.82,
     // profiles/r02_upsample_small_factor_ab.txt)
     double2 ty_next = make_double2(0.0, 0.0);
+    // Shared-space addresses of the row tables, pinned in registers: left to itself the compiler re-derives them (S2R
+    // SR_CgaCtaId, LDC, MOV, LEA) at every window step of the sweep (FP64 bicubic 2x2: 0.505 -> 0.495 ms at 8192^2;
+    // for the FP32 window kernel of factor 1 the same was mixed -- 1x1 0.77 -> 0.79, 4x1 -0.6 % -- and is not used).
+    [[maybe_unused]] uint32_t sty_addr = static_cast<uint32_t>(__cvta_generic_to_shared(s_ty));
+    [[maybe_unused]] uint32_t stop_addr = static_cast<uint32_t>(__cvta_generic_to_shared(s_top));
+    if constexpr (kF64 && kCubic) asm volatile("" : "+r"(sty_addr), "+r"(stop_addr));
     int top_next = 0;
     // The same for the FP32 window-load kernel of longitude factor 1 (2x1 0.84 -> 0.91, 1x1 0.72 -> 0.77, 4x1 0.97 -> 0.99); the
     // factor-2 form LOSES with it (2x2 0.98 -> 0.94: eight more spill bytes inside its loop), so it keeps loading in place.
@@ -321,7 +327,9 @@ upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
         T v[COLS];
         if constexpr (kF64 && kCubic) {
             const double2 ty2 = ty_next;
-            ty_next = s_ty[jr + 1]; top_next = s_top[jr + 1];      // one entry of slack behind the last row
+            // s_ty[jr + 1], s_top[jr + 1]: one entry of slack behind the last row
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ty_next.x), "=d"(ty_next.y) : "r"(sty_addr + (jr + 1) * 16));
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(top_next) : "r"(stop_addr + (jr + 1) * 4));
 #pragma unroll
             for (int c = 0; c < COLS; ++c) {
                 v[c] = catmull_rom_eval(vk[c], h[(ph + 1) % TAPS][c], ty2.x, ty2.y);
