@@ -25,9 +25,13 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 decode_raw_kernel(const unsigned char* __restrict__ raw, int nc_type, int big_endian, int flip_rows, double scale,
                   double offset, int n_lat, int n_lon, T* __restrict__ out, int64_t ld) {
-    const int64_t total = static_cast<int64_t>(n_lat) * n_lon;
-    for (int64_t k = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; k < total; k += static_cast<int64_t>(gridDim.x) * 256) {
-        const int r = static_cast<int>(k / n_lon), c = static_cast<int>(k - static_cast<int64_t>(r) * n_lon);
+    // a work item is 256 consecutive cells of one row: one division per item, none per cell
+    const int chunks = (n_lon + 255) / 256;
+    const int64_t items = static_cast<int64_t>(n_lat) * chunks;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+        const int r = static_cast<int>(it / chunks), c = static_cast<int>(it - static_cast<int64_t>(r) * chunks) * 256 + static_cast<int>(threadIdx.x);
+        if (c >= n_lon) continue;
+        const int64_t k = static_cast<int64_t>(r) * n_lon + c;
         double v;
         if (nc_type == 3) {
             uint16_t u = __ldg(reinterpret_cast<const uint16_t*>(raw) + k);
