@@ -39,6 +39,9 @@ constexpr int kColThreads = 128;   // threads along the output columns; each own
 constexpr int kRowGroups = 2;      // row halves of a tile, swept by separate thread groups
 constexpr int kTileThreads = kColThreads * kRowGroups;
 constexpr int kTileRowsMax = 128;  // output rows per CTA (upper bound; host picks TJ <= this)
+#ifndef AUVI_F64_MINB
+#define AUVI_F64_MINB 3        // resident CTAs per SM the FP64 kernels are compiled for (4 = 64 registers: measured, lost -- DESIGN.md section 10)
+#endif
 
 struct AxisDev {
     const double* coord;
@@ -108,9 +111,6 @@ __device__ __noinline__ T lattice_cell_exact(const TileParams<T>* p, int64_t J, 
 // (window_mode) and launches the generic form otherwise.  A zero weight on a NaN tap yields NaN: such an output goes to the
 // exact re-evaluation like any other dirty one.
 template <typename T, int METHOD, int WIN = 0>
-#ifndef AUVI_F64_MINB
-#define AUVI_F64_MINB 3
-#endif
 __global__ void __launch_bounds__(kTileThreads, sizeof(T) == 4 ? 4 : AUVI_F64_MINB)
 upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileParams<T> p) {
     constexpr bool kCubic = (METHOD == CUBIC);
