@@ -877,31 +877,30 @@ constexpr int kBBH = kBH + 2 * kBHaloR;        // 36
 constexpr int kBThreads = 256;
 
 // mean_valid4 (exact.cuh, GridH.cpp:10-18) without branches, for the streaming kernel below where every lane takes it with
-// its own count: the sum gathers the valid corners in the order a, b, c, d by predicated adds; the division by the count
-// is the product with 1 / n -- exact for n = 1, 2, 4, and for n = 3 the same Markstein step as div_count (r = s - 3q exact
-// in an FMA, q' = RN(q + r * RN(1/3)) is the correctly rounded quotient), which leaves q alone when r = 0.  Same bits.
-__device__ __forceinline__ void add_if_number(double& s, float v) {
-    const double vd = static_cast<double>(v);
-    asm("{\n\t.reg .pred p;\n\tsetp.num.f32 p, %1, %1;\n\t@p add.rn.f64 %0, %0, %2;\n\t}" : "+d"(s) : "f"(v), "d"(vd));
-}
-__device__ __forceinline__ void add_if_number(double& s, double v) {
-    asm("{\n\t.reg .pred p;\n\tsetp.num.f64 p, %1, %1;\n\t@p add.rn.f64 %0, %0, %1;\n\t}" : "+d"(s) : "d"(v));
-}
+// its own count.  The sum adds +0.0 in place of a missing corner: s + (+0.0) == s for every s but -0.0, and s is never -0.0
+// here (it starts at +0.0, and +0.0 + (-0.0) = +0.0), so the bits are those of the reference's "skip the NaNs" loop.  The
+// division by the count is the product with 1 / n from a five-entry table -- exact for n = 1, 2, 4; for n = 3 the same
+// Markstein step as div_count (r = s - 3q exact in an FMA, q' = RN(q + r * RN(1/3)) is the correctly rounded quotient),
+// which leaves q alone when r = 0; n = 0 multiplies by NaN.  Same bits as mean_valid4 (A/B: sha1 of whole filled grids).
+__constant__ double kInvCount[5] = {__builtin_nan(""), 1.0, 0.5, 0.33333333333333331, 0.25};
+__constant__ double kCount[5] = {0.0, 1.0, 2.0, 3.0, 4.0};
 __device__ __noinline__ double ddiv_cold(double a, double b) { return ddiv(a, b); }   // out of line: never speculated into the stream
 template <typename T>
 __device__ __forceinline__ double mean_valid4_flat(T a, T b, T c, T d) {
-    const int n = static_cast<int>(a == a) + static_cast<int>(b == b) + static_cast<int>(c == c) + static_cast<int>(d == d);
-    double s = 0.0;
-    add_if_number(s, a); add_if_number(s, b); add_if_number(s, c); add_if_number(s, d);
-    const int e = (n >> 1) << 20;                                  // n = 1, 2, 4 -> exponent steps 0, 1, 2
-    const double inv = n == 3 ? 0.33333333333333331 : __hiloint2double(0x3ff00000 - e, 0);
-    const double cnt = n == 3 ? 3.0 : __hiloint2double(0x3ff00000 + e, 0);
+    const bool va = a == a, vb = b == b, vc = c == c, vd = d == d;
+    const int n = static_cast<int>(va) + static_cast<int>(vb) + static_cast<int>(vc) + static_cast<int>(vd);
+    const T zero = static_cast<T>(0);
+    double s = dadd(0.0, static_cast<double>(va ? a : zero));
+    s = dadd(s, static_cast<double>(vb ? b : zero));
+    s = dadd(s, static_cast<double>(vc ? c : zero));
+    s = dadd(s, static_cast<double>(vd ? d : zero));
+    const double inv = kInvCount[n], cnt = kCount[n];
     double q = dmul(s, inv);
     const double r = __fma_rn(-cnt, q, s);
     q = __fma_rn(r, inv, q);
     const double mag = fabs(s);
     if (!(mag > 1e-280 && mag < 1e300) && s != 0.0) q = ddiv_cold(s, cnt);   // where q or r could go subnormal / overflow: the division itself
-    return n ? q : qnan();
+    return q;
 }
 
 constexpr int kNoCell = -(1 << 30);            // x0 table entry of a query whose position is NaN (out of bounds)
