@@ -886,7 +886,7 @@ __constant__ double kInvCount[5] = {__builtin_nan(""), 1.0, 0.5, 0.3333333333333
 __constant__ double kCount[5] = {0.0, 1.0, 2.0, 3.0, 4.0};
 __device__ __noinline__ double ddiv_cold(double a, double b) { return ddiv(a, b); }   // out of line: never speculated into the stream
 template <typename T>
-__device__ __forceinline__ double mean_valid4_flat(T a, T b, T c, T d) {
+__device__ __forceinline__ double mean_valid4_flat(T a, T b, T c, T d, int& n_valid) {
     const bool va = a == a, vb = b == b, vc = c == c, vd = d == d;
     const int n = static_cast<int>(va) + static_cast<int>(vb) + static_cast<int>(vc) + static_cast<int>(vd);
     const T zero = static_cast<T>(0);
@@ -894,6 +894,7 @@ __device__ __forceinline__ double mean_valid4_flat(T a, T b, T c, T d) {
     s = dadd(s, static_cast<double>(vb ? b : zero));
     s = dadd(s, static_cast<double>(vc ? c : zero));
     s = dadd(s, static_cast<double>(vd ? d : zero));
+    n_valid = n;
     const double inv = kInvCount[n], cnt = kCount[n];
     double q = dmul(s, inv);
     const double r = __fma_rn(-cnt, q, s);
@@ -977,35 +978,41 @@ bilinear_fill_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         const int nrows = static_cast<int>(min(static_cast<int64_t>(kBH), p.row_end - J0));
         const int ncols = min(kBW, p.n_out_cols - I0);
         T* const out_tile = p.out + (J0 - p.row_begin) * p.out_ld + I0;
-        for (int k = tid; k < nrows * VPR; k += kBThreads) {
-            const int lj = k / VPR, col = (k - lj * VPR) * VEC;
-            if (col >= ncols) continue;
+        // A thread keeps its column group for the whole tile (kBThreads is a multiple of the vectors per row): the corner
+        // columns of its cells -- offsets into a tile row, kNoCell where the query is out of bounds -- are formed once.
+        static_assert(kBThreads % VPR == 0, "a thread's column group is fixed");
+        const int col = (tid % VPR) * VEC;
+        int xo0[VEC], xo1[VEC];
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+            const int x0 = col + c < kBW ? s.x0[col + c] : kNoCell;
+            xo0[c] = x0 == kNoCell ? kNoCell : x0 - c0;
+            xo1[c] = min(x0 + 1, p.g.n_lon - 1) - c0;
+        }
+        for (int lj = tid / VPR; lj < nrows && col < ncols; lj += kBThreads / VPR) {
             const T* const src = tl + (lj + kBHaloR) * kBBW + kBHaloC + col;
             T v[VEC];
             if constexpr (sizeof(T) == 4) { const float4 q = *reinterpret_cast<const float4*>(src); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
             else { const double2 q = *reinterpret_cast<const double2*>(src); v[0] = q.x; v[1] = q.y; }
             const double y = s.y[lj];
             const int y0 = s.y0[lj], y1 = min(y0 + 1, p.g.n_lat - 1);
-            const T* const r0p = tl + (y0 - r0) * kBBW - c0;
-            const T* const r1p = tl + (y1 - r0) * kBBW - c0;
+            const T* const r0p = tl + (y0 - r0) * kBBW;
+            const T* const r1p = tl + (y1 - r0) * kBBW;
             const bool y_ok = !isnan(y);
 #pragma unroll
             for (int c = 0; c < VEC; ++c) {
                 if (v[c] == v[c]) continue;                         // valid cell: passes through
-                const int li = col + c;
-                const int x0 = s.x0[li];                            // kNoCell: the query is out of bounds (x is NaN)
                 double result = qnan();
-                if (y_ok && x0 != kNoCell) {
-                    const int x1 = min(x0 + 1, p.g.n_lon - 1);
-                    const T a = r0p[x0], b = r0p[x1], cc = r1p[x0], d = r1p[x1];
+                if (y_ok && xo0[c] != kNoCell) {
+                    const T a = r0p[xo0[c]], b = r0p[xo1[c]], cc = r1p[xo0[c]], d = r1p[xo1[c]];
                     // A masked cell queried at its own node is one of its four corners (floor() of the node position is the
                     // node or, by FP64 noise, the one below: SURVEY.md section 0 fact 3), so this is the NaN-corner mean
                     // (GridH.cpp:186-198) for every query of a gap fill; the lerp stays reachable, out of line.
-                    if (a != a || b != b || cc != cc || d != d)
-                        result = mean_valid4_flat<T>(a, b, cc, d);
-                    else
+                    int n_valid;
+                    result = mean_valid4_flat<T>(a, b, cc, d, n_valid);
+                    if (n_valid == 4)
                         result = bilinear_lerp_cold(static_cast<double>(a), static_cast<double>(b), static_cast<double>(cc), static_cast<double>(d),
-                                                    s.x[li], y, x0, y0);
+                                                    s.x[col + c], y, xo0[c] + c0, y0);
                 }
                 v[c] = static_cast<T>(result);
             }
