@@ -116,10 +116,10 @@ __device__ double exact_bilinear(const GridView<T>& g, double x, double y) {
 //     th = t/2 (exact) and 2*p1 becomes p1 -- RN(RN(RN(p1 + lin/2) + quad/2) + cub/2) is half the reference's sum.
 // Checked bit for bit against the literal expression on 2e8 inputs (signed zeros, t = 0, t within 1e-12 of 0 and 1).
 __device__ __forceinline__ double catmull_rom_exact_h(double p0, double p1, double p2, double p3, double t, double th) {
-    const double lin = dmul(dadd(-p0, p2), th);
+    const double lin = dmul(dsub(p2, p0), th);                    // p2 - p0 == -p0 + p2, 3*p1 - p0 == -p0 + 3*p1: same reals, same roundings
     const double qc = dsub(__fma_rn(4.0, p2, __fma_rn(2.0, p0, -dmul(5.0, p1))), p3);
     const double quad = dmul(dmul(qc, t), th);
-    const double cc = dadd(dsub(dadd(-p0, dmul(3.0, p1)), dmul(3.0, p2)), p3);
+    const double cc = dadd(dsub(dsub(dmul(3.0, p1), p0), dmul(3.0, p2)), p3);
     const double cub = dmul(dmul(dmul(cc, t), t), th);
     return dadd(dadd(dadd(p1, lin), quad), cub);
 }
@@ -128,9 +128,12 @@ __device__ __forceinline__ double catmull_rom_exact_h(double p0, double p1, doub
 struct CatmullCoef { double a, qc, cc; };
 __device__ __forceinline__ CatmullCoef catmull_rom_coef(double p0, double p1, double p2, double p3) {
     CatmullCoef k;
-    k.a = dadd(-p0, p2);
+    // p2 - p0 and 3*p1 - p0 are the reference's -p0 + p2 and -p0 + 3*p1 (the same real numbers, so the same roundings, signed
+    // zeros included); spelled with the negation the compiler materialised -p0 with an FP64 add of its own (one operation in
+    // eleven on a pipe-bound kernel)
+    k.a = dsub(p2, p0);
     k.qc = dsub(__fma_rn(4.0, p2, __fma_rn(2.0, p0, -dmul(5.0, p1))), p3);
-    k.cc = dadd(dsub(dadd(-p0, dmul(3.0, p1)), dmul(3.0, p2)), p3);
+    k.cc = dadd(dsub(dsub(dmul(3.0, p1), p0), dmul(3.0, p2)), p3);
     return k;
 }
 __device__ __forceinline__ double catmull_rom_eval(const CatmullCoef& k, double p1, double t, double th) {
