@@ -111,7 +111,7 @@ __device__ __noinline__ T lattice_cell_exact(const TileParams<T>* p, int64_t J, 
 // (window_mode) and launches the generic form otherwise.  A zero weight on a NaN tap yields NaN: such an output goes to the
 // exact re-evaluation like any other dirty one.
 template <typename T, int METHOD, int WIN = 0>
-__global__ void __launch_bounds__(kTileThreads, sizeof(T) == 4 ? 4 : AUVI_F64_MINB)
+__global__ void __launch_bounds__(kTileThreads, sizeof(T) == 4 ? (WIN == 1 ? 3 : 4) : AUVI_F64_MINB)   // WIN = 1: wide boxes, <= 3 CTAs fit an SM anyway
 upsample_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileParams<T> p) {
     constexpr bool kCubic = (METHOD == CUBIC);
     static_assert(WIN == 0 || (METHOD == CUBIC && sizeof(T) == 4), "window loads: FP32 bicubic only");
